@@ -1,0 +1,150 @@
+/*
+ * mems_b200.h -- C ABI of the B200-native batched surrogate Metropolis-Hastings path.
+ *
+ * The reference (filippozacchei/MCMC-MEMS) is pure Python and has no FFI of its own;
+ * the boundary below is what a binding for its hot path has to offer.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * tree; "cuqi" = the un-vendored dependency cuqipy==0.8.0, README.md:36).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types cross the boundary;
+ *   - every function returns 0 on success or a negative MEMS_E_* code; the message
+ *     of the last failure on the calling thread is mems_last_error();
+ *   - "host" arrays are read during the call and copied; "device" arrays are CUDA
+ *     device pointers on the handle's device and must stay valid until the stream
+ *     reaches the end of the enqueued work;
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream`
+ *     (NULL = the legacy default stream); calls do not synchronise unless stated;
+ *   - one handle per device, not thread-safe per handle;
+ *   - there is no CPU fallback: without a usable sm_100 device mems_create fails.
+ *
+ * Per-chain arrays are stored parameter-major, chain-minor ("[P][C]": element
+ * (p, c) at p*C + c) so that consecutive chains are consecutive in memory.
+ */
+#ifndef MEMS_B200_H
+#define MEMS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MEMS_PMAX 4          /* max number of sampled parameters (reference uses 3 and 4) */
+#define MEMS_WIDTH 64        /* hidden width of the surrogate (config_I.json: N_NEURONS)  */
+#define MEMS_HIDDEN 6        /* number of tanh layers (config_I.json: N_LAYERS)           */
+
+#define MEMS_PATH_FP32 0     /* CUDA-core FP32 check path (parity reference on the GPU)   */
+#define MEMS_PATH_TC   1     /* tcgen05 split-FP16 tensor-core path (the product path)    */
+
+#define MEMS_OK             0
+#define MEMS_E_INVALID     -1   /* bad argument / shape                */
+#define MEMS_E_CUDA        -2   /* CUDA runtime error                  */
+#define MEMS_E_STATE       -3   /* call order (weights/problem/chains) */
+#define MEMS_E_UNSUPPORTED -4   /* device or configuration unsupported */
+
+typedef struct MemsConfig {
+    int32_t n_params;   /* P: sampled parameters = surrogate inputs minus the time column */
+    int32_t n_time;     /* T: time points per signal (len(data_processor.time))           */
+    int32_t n_chains;   /* C: independent chains resident on this device                  */
+    int32_t path;       /* MEMS_PATH_FP32 or MEMS_PATH_TC                                 */
+    int32_t device;     /* CUDA device ordinal                                            */
+    int32_t chains_per_block; /* 0 = choose; else power of two <= 128                     */
+    int32_t reserved[2];
+} MemsConfig;
+
+typedef struct MemsHandle_* mems_handle_t;
+
+const char* mems_last_error(void);
+int  mems_version(void);
+
+/* Lifetime.  Replaces: the notebook-level objects built once per run
+ * (tests/Xaccelerometer_geometric/identification.ipynb cells 8-14). */
+int  mems_create(const MemsConfig* cfg, mems_handle_t* out);
+void mems_destroy(mems_handle_t h);
+
+/* Surrogate weights.  Replaces NN_Model.load_model (src/SurrogateModeling/model.py:28-34):
+ * the Keras Dense stack [P+1]->64 x6 tanh ->1 in Keras layout kernel[in][out], float32.
+ * W[0]: (P+1) x 64, W[1..5]: 64 x 64, W[6]: 64 x 1;  b[0..5]: 64, b[6]: 1.   HOST pointers. */
+int  mems_set_weights(mems_handle_t h, const float* const* W, const float* const* b);
+
+/* Problem constants.  Replaces the closure state of create_forward_model_function
+ * (src/InverseProblems/utils.py:22-28: time grid, StandardScaler mean_/scale_) and the
+ * cuqi objects of identification.ipynb cell 10/14: Gaussian likelihood (y_obs, sigma2 = the
+ * iid noise variance), Uniform prior (low, high) and the Gaussian proposal (chol = lower
+ * Cholesky factor of its covariance, row-major P x P).                      HOST pointers.
+ * time[T], scaler_mean[P+1], scaler_scale[P+1], y_obs[T], low[P], high[P], chol[P*P]. */
+int  mems_set_problem(mems_handle_t h, const double* time, const double* scaler_mean,
+                      const double* scaler_scale, const double* y_obs, double sigma2,
+                      const double* low, const double* high, const double* chol);
+
+/* Forward model + log-likelihood for n parameter vectors.  Replaces forward_model(x)
+ * (src/InverseProblems/utils.py:30-40) and Gaussian(...).logd(y_obs) (identification.ipynb:169).
+ * x_dev [P][n] (device, f64).  y_out [n][T] (device, f32) and loglik_out [n] (device, f64) may
+ * each be NULL.  loglik = -0.5 * sum_t (y_obs - f)^2 / sigma2, i.e. WITHOUT the additive
+ * constant -0.5*T*(log sigma2 + log 2pi) and without the prior term. */
+int  mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out,
+                  double* loglik_out, void* stream);
+
+/* Chain initialisation.  Replaces MH(target, proposal, x0) + the first lines of
+ * cuqi MH._sample_adapt (samples[:,0]=x0, target_eval[0]=logd(x0), acc[0]=1, scale=0.1):
+ * x0_dev [P][C] (device, f64); scale0 = initial proposal scale; seed = Philox key.
+ * chain_id0 = global id of this device's first chain (Philox counters carry global ids so
+ * results do not depend on how chains are sharded over GPUs). */
+int  mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint64_t seed,
+                      uint64_t chain_id0, void* stream);
+
+/* n_steps Metropolis-Hastings updates of every chain with device-side Philox randomness.
+ * Replaces the hot loop of cuqi MH._sample_adapt / MH._sample driven from
+ * identification.ipynb:302 (single_update: x* = x + scale*xi, accept iff
+ * log u <= min(0, l* - l)).  adapt_window = Na (= int(0.1*N) in cuqi; 0 = frozen scale).
+ * After every `thin`-th update of this call the state is written:
+ *   samples_out [n_steps/thin][P][C] (device, f64, may be NULL),
+ *   loglik_out  [n_steps/thin][C]    (device, f64, may be NULL; same convention as mems_forward,
+ *                                     -inf never occurs for a stored state unless x0 was outside). */
+int  mems_run(mems_handle_t h, int32_t n_steps, int32_t adapt_window, int32_t thin,
+              double* samples_out, double* loglik_out, void* stream);
+
+/* Same update with caller-supplied randomness (parity mode, no Philox):
+ * xi [n_steps][P][C] (device, f64; already-correlated proposal increments, x* = x + scale*xi),
+ * log_u [n_steps][C] (device, f64).  Outputs (device, each may be NULL):
+ * samples_out [n_steps][P][C] f64, loglik_prop_out [n_steps][C] f64 (proposal log-likelihood,
+ * -inf when the proposal is outside the prior box), decisions_out [n_steps][C] u8. */
+int  mems_run_explicit(mems_handle_t h, int32_t n_steps, int32_t adapt_window,
+                       const double* xi, const double* log_u, double* samples_out,
+                       double* loglik_prop_out, uint8_t* decisions_out, void* stream);
+
+/* The randomness mems_run would consume for updates [step0, step0+n_steps) of every chain:
+ * xi_out [n_steps][P][C] = chol * z (f64), log_u_out [n_steps][C] (f64).  Device pointers. */
+int  mems_draw(mems_handle_t h, uint64_t step0, int32_t n_steps, double* xi_out,
+               double* log_u_out, void* stream);
+
+/* Current chain state (device pointers, each may be NULL): x [P][C] f64, loglik [C] f64,
+ * scale [C] f64 (cuqi's self.scale), accept_count [C] u32 (accepted updates since init, the
+ * initial acc[0]=1 not included), steps_done (HOST pointer, synchronises the stream). */
+int  mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale,
+                    uint32_t* accept_count, uint64_t* steps_done, void* stream);
+
+/* Generic Dense-stack inference.  Replaces NN_Model.predict / nn_model.model(X)
+ * (src/SurrogateModeling/model.py:142-151, src/InverseProblems/utils.py:39) for any of the
+ * reference's Sequential models: n_layers Dense layers, widths[0..n_layers] (input width
+ * first, all <= 64), tanh on every layer except the last.  W/b are HOST pointer arrays
+ * (Keras layout), X_dev [n][widths[0]] f32 and Y_dev [n][widths[n_layers]] f32 device pointers. */
+int  mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths,
+                      const float* const* W, const float* const* b, const float* X_dev,
+                      int64_t n, float* Y_dev, void* stream);
+
+/* Hardware self-test of the tensor-core plumbing the MH kernels rely on (UMMA descriptors,
+ * 128B swizzle, TMEM operand packing, tcgen05.ld/st, commit->mbarrier):
+ * D[128][64] (f32) = A[128][64] (f16) * B[64][64]^T (f16), all device pointers, row-major.
+ * variant 0: A operand written to TMEM by the threads (the product path), 1: A from shared memory. */
+int  mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev,
+                        const void* b_f16_dev, float* d_out_dev, void* stream);
+
+/* Number of kernel launches issued through this handle since creation (bench bookkeeping). */
+int64_t mems_launch_count(mems_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMS_B200_H */

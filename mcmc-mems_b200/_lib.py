@@ -1,0 +1,77 @@
+"""ctypes binding of ``libmems_b200.so`` (C ABI: include/mems_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is
+no CPU fallback: if the library is missing or no sm_100 device is present every compute entry
+point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmems_b200.so")
+
+MEMS_PMAX = 4
+MEMS_WIDTH = 64
+MEMS_HIDDEN = 6
+PATH_FP32 = 0
+PATH_TC = 1
+
+EXPORTS = [
+    "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
+    "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
+    "mems_draw", "mems_get_state", "mems_mlp_forward", "mems_launch_count", "mems_selftest_umma",
+]
+
+
+class MemsConfig(C.Structure):
+    _fields_ = [("n_params", C.c_int32), ("n_time", C.c_int32), ("n_chains", C.c_int32),
+                ("path", C.c_int32), ("device", C.c_int32), ("chains_per_block", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+class MemsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MemsError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
+    L.mems_last_error.restype = C.c_char_p
+    L.mems_last_error.argtypes = []
+    L.mems_version.restype = C.c_int
+    L.mems_create.argtypes = [C.POINTER(MemsConfig), C.POINTER(vp)]
+    L.mems_destroy.argtypes = [vp]
+    L.mems_destroy.restype = None
+    L.mems_set_weights.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mems_set_problem.argtypes = [vp, vp, vp, vp, vp, dbl, vp, vp, vp]
+    L.mems_forward.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.mems_init_chains.argtypes = [vp, vp, dbl, u64, u64, vp]
+    L.mems_run.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.mems_run_explicit.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mems_draw.argtypes = [vp, u64, i32, vp, vp, vp]
+    L.mems_get_state.argtypes = [vp, vp, vp, vp, vp, C.POINTER(u64), vp]
+    L.mems_mlp_forward.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), vp, i64, vp, vp]
+    L.mems_launch_count.argtypes = [vp]
+    L.mems_launch_count.restype = i64
+    L.mems_selftest_umma.argtypes = [i32, i32, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().mems_last_error().decode("utf-8", "replace")
+        raise MemsError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,372 @@
+// C ABI of the batched surrogate-MH path (see include/mems_b200.h for the contract and the
+// reference interfaces each entry point replaces).  Host-side only: argument checking, constant
+// preparation (scaled time column, split-FP16 weight image) and kernel launches.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "mems_common.cuh"
+
+int mems_mlp_forward_launch(int n_layers, const int* widths, const float* const* Wd, const float* const* bd,
+                            const float* X, long long n, float* Y, int sm_count, cudaStream_t st);
+size_t mems_tc_wimg_bytes();
+void mems_tc_build_wimg(const MemsProblem& pb, void* host_img);
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return fail(MEMS_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));           \
+    } while (0)
+
+}  // namespace
+
+struct MemsHandle_ {
+    MemsConfig cfg;
+    int sm_count = 0;
+    MemsProblem host_pb;
+    MemsProblem* dev_pb = nullptr;
+    float* dev_ts = nullptr;
+    double* dev_yobs = nullptr;
+    void* dev_wimg = nullptr;
+    MemsChains chains;
+    bool have_weights = false, have_problem = false, have_chains = false;
+    unsigned long long steps_done = 0;
+    long long launches = 0;
+};
+
+namespace {
+
+int choose_nc(const MemsHandle_* h, int C) {
+    if (h->cfg.chains_per_block > 0) return h->cfg.chains_per_block;
+    int best = 1;
+    long long best_cost = -1;
+    for (int nc = 1; nc <= MEMS_NCMAX; nc <<= 1) {
+        const long long nbatch = (C + nc - 1) / nc;
+        const long long rounds = (nbatch + h->sm_count - 1) / h->sm_count;
+        const long long cost = rounds * nc;
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nc; }
+    }
+    return best;
+}
+
+int upload_problem(MemsHandle_* h) {
+    h->host_pb.ts = h->dev_ts;
+    h->host_pb.yobs = h->dev_yobs;
+    h->host_pb.wimg = reinterpret_cast<const uint4*>(h->dev_wimg);
+    CUDA_TRY(cudaMemcpy(h->dev_pb, &h->host_pb, sizeof(MemsProblem), cudaMemcpyHostToDevice));
+    return MEMS_OK;
+}
+
+MemsLaunchCtx make_ctx(MemsHandle_* h, void* stream) {
+    MemsLaunchCtx ctx;
+    ctx.pb_dev = h->dev_pb;
+    ctx.pb_host = &h->host_pb;
+    ctx.chains = h->chains;
+    ctx.sm_count = h->sm_count;
+    ctx.stream = reinterpret_cast<cudaStream_t>(stream);
+    return ctx;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mems_last_error(void) { return g_err; }
+int mems_version(void) { return 100; }
+
+int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
+    if (!cfg || !out) return fail(MEMS_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->n_params < 1 || cfg->n_params > MEMS_PMAX)
+        return fail(MEMS_E_INVALID, "n_params=%d outside [1,%d]", cfg->n_params, MEMS_PMAX);
+    if (cfg->n_time < 1 || cfg->n_time > 4096) return fail(MEMS_E_INVALID, "n_time=%d outside [1,4096]", cfg->n_time);
+    if (cfg->n_chains < 1) return fail(MEMS_E_INVALID, "n_chains=%d must be >= 1", cfg->n_chains);
+    if (cfg->path != MEMS_PATH_FP32 && cfg->path != MEMS_PATH_TC) return fail(MEMS_E_INVALID, "unknown path %d", cfg->path);
+    if (cfg->chains_per_block != 0) {
+        const int v = cfg->chains_per_block;
+        if (v < 1 || v > MEMS_NCMAX || (v & (v - 1))) return fail(MEMS_E_INVALID, "chains_per_block must be a power of two <= %d", MEMS_NCMAX);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MEMS_E_UNSUPPORTED, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(MEMS_E_INVALID, "device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(MEMS_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    MemsHandle_* h = new (std::nothrow) MemsHandle_();
+    if (!h) return fail(MEMS_E_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    memset(&h->host_pb, 0, sizeof(MemsProblem));
+    h->host_pb.P = cfg->n_params;
+    h->host_pb.T = cfg->n_time;
+    const size_t C = (size_t)cfg->n_chains, P = (size_t)cfg->n_params;
+    memset(&h->chains, 0, sizeof(MemsChains));
+    h->chains.C = cfg->n_chains;
+    bool ok = cudaMalloc(&h->dev_pb, sizeof(MemsProblem)) == cudaSuccess &&
+              cudaMalloc(&h->dev_ts, sizeof(float) * cfg->n_time) == cudaSuccess &&
+              cudaMalloc(&h->dev_yobs, sizeof(double) * cfg->n_time) == cudaSuccess &&
+              cudaMalloc(&h->dev_wimg, mems_tc_wimg_bytes()) == cudaSuccess &&
+              cudaMalloc(&h->chains.x, sizeof(double) * P * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.ll, sizeof(double) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.scale, sizeof(double) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.lambda, sizeof(double) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.win_acc, sizeof(int) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.adapt_i, sizeof(int) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.acc_count, sizeof(unsigned int) * C) == cudaSuccess;
+    if (!ok) {
+        const char* msg = cudaGetErrorString(cudaGetLastError());
+        mems_destroy(h);
+        return fail(MEMS_E_CUDA, "device allocation failed: %s", msg);
+    }
+    *out = h;
+    return MEMS_OK;
+}
+
+void mems_destroy(mems_handle_t h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->dev_pb); cudaFree(h->dev_ts); cudaFree(h->dev_yobs); cudaFree(h->dev_wimg);
+    cudaFree(h->chains.x); cudaFree(h->chains.ll); cudaFree(h->chains.scale); cudaFree(h->chains.lambda);
+    cudaFree(h->chains.win_acc); cudaFree(h->chains.adapt_i); cudaFree(h->chains.acc_count);
+    delete h;
+}
+
+int mems_set_weights(mems_handle_t h, const float* const* W, const float* const* b) {
+    if (!h || !W || !b) return fail(MEMS_E_INVALID, "null argument");
+    for (int l = 0; l <= MEMS_HIDDEN; ++l)
+        if (!W[l] || !b[l]) return fail(MEMS_E_INVALID, "null weight pointer for layer %d", l);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MemsProblem& pb = h->host_pb;
+    const int P = pb.P;
+    memcpy(pb.W1, W[0], sizeof(float) * (P + 1) * MEMS_WIDTH);
+    memcpy(pb.b1, b[0], sizeof(float) * MEMS_WIDTH);
+    for (int l = 0; l < MEMS_NLAYER_H; ++l) {
+        memcpy(pb.Wh + l * MEMS_WIDTH * MEMS_WIDTH, W[l + 1], sizeof(float) * MEMS_WIDTH * MEMS_WIDTH);
+        memcpy(pb.bh + l * MEMS_WIDTH, b[l + 1], sizeof(float) * MEMS_WIDTH);
+    }
+    memcpy(pb.w7, W[MEMS_HIDDEN], sizeof(float) * MEMS_WIDTH);
+    pb.b7 = b[MEMS_HIDDEN][0];
+    std::vector<unsigned char> img(mems_tc_wimg_bytes());
+    mems_tc_build_wimg(pb, img.data());
+    CUDA_TRY(cudaMemcpy(h->dev_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+    h->have_weights = true;
+    return upload_problem(h);
+}
+
+int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_mean, const double* scaler_scale,
+                     const double* y_obs, double sigma2, const double* low, const double* high, const double* chol) {
+    if (!h || !time || !scaler_mean || !scaler_scale || !y_obs || !low || !high || !chol)
+        return fail(MEMS_E_INVALID, "null argument");
+    if (!(sigma2 > 0.0)) return fail(MEMS_E_INVALID, "sigma2 must be positive");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MemsProblem& pb = h->host_pb;
+    const int P = pb.P, T = pb.T;
+    for (int p = 0; p <= P; ++p) {
+        if (!(scaler_scale[p] != 0.0)) return fail(MEMS_E_INVALID, "scaler_scale[%d] is zero", p);
+        pb.mean[p] = scaler_mean[p];
+        pb.sscale[p] = scaler_scale[p];
+    }
+    for (int p = 0; p < P; ++p) {
+        if (!(low[p] <= high[p])) return fail(MEMS_E_INVALID, "low[%d] > high[%d]", p, p);
+        pb.low[p] = low[p];
+        pb.high[p] = high[p];
+    }
+    for (int i = 0; i < P * P; ++i) pb.chol[i] = chol[i];
+    pb.sigma2 = sigma2;
+    pb.neg_half_inv_sigma2 = -0.5 / sigma2;
+    std::vector<float> ts(T);
+    // StandardScaler.transform on the time column in f64, then the Keras cast to f32 (utils.py:38-39)
+    for (int t = 0; t < T; ++t) ts[t] = (float)((time[t] - scaler_mean[P]) / scaler_scale[P]);
+    CUDA_TRY(cudaMemcpy(h->dev_ts, ts.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(h->dev_yobs, y_obs, sizeof(double) * T, cudaMemcpyHostToDevice));
+    h->have_problem = true;
+    return upload_problem(h);
+}
+
+int mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out, double* loglik_out, void* stream) {
+    if (!h || !x_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (!h->have_weights || !h->have_problem) return fail(MEMS_E_STATE, "set weights and problem first");
+    if (n < 0) return fail(MEMS_E_INVALID, "n < 0");
+    if (n == 0) return MEMS_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MemsLaunchCtx ctx = make_ctx(h, stream);
+    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, x_dev, n, y_out, loglik_out, 0)
+                                                : mems_fp32_forward(ctx, x_dev, n, y_out, loglik_out, 0);
+    h->launches += 1;
+    if (e != 0) return fail(MEMS_E_CUDA, "forward launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+namespace {
+__global__ void init_chains_kernel(MemsChains ch, int P, const double* x0, double scale0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ch.C) return;
+    for (int p = 0; p < P; ++p) ch.x[(size_t)p * ch.C + c] = x0[(size_t)p * ch.C + c];
+    ch.scale[c] = scale0;
+    ch.lambda[c] = scale0;
+    ch.win_acc[c] = 1;          // cuqi: acc[0] = 1 belongs to the first adaptation window
+    ch.adapt_i[c] = 0;
+    ch.acc_count[c] = 0u;
+}
+}  // namespace
+
+int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint64_t seed, uint64_t chain_id0,
+                     void* stream) {
+    if (!h || !x0_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (!h->have_weights || !h->have_problem) return fail(MEMS_E_STATE, "set weights and problem first");
+    if (!(scale0 > 0.0)) return fail(MEMS_E_INVALID, "scale0 must be positive");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->chains.seed = seed;
+    h->chains.chain_id0 = chain_id0;
+    h->steps_done = 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int C = h->chains.C;
+    init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.P, x0_dev, scale0);
+    CUDA_TRY(cudaGetLastError());
+    MemsLaunchCtx ctx = make_ctx(h, stream);
+    // target_eval[0] = logd(x0): likelihood + prior (-inf outside the box)
+    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1)
+                                                : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1);
+    h->launches += 2;
+    if (e != 0) return fail(MEMS_E_CUDA, "init launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->have_chains = true;
+    return MEMS_OK;
+}
+
+static int run_common(mems_handle_t h, MemsRunArgs& ra, void* stream) {
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    ra.step0 = h->steps_done;
+    ra.nc = choose_nc(h, h->chains.C);
+    MemsLaunchCtx ctx = make_ctx(h, stream);
+    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_run(ctx, ra) : mems_fp32_run(ctx, ra);
+    h->launches += 1;
+    if (e != 0) return fail(MEMS_E_CUDA, "run launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    h->steps_done += (unsigned long long)ra.n_steps;
+    return MEMS_OK;
+}
+
+int mems_run(mems_handle_t h, int32_t n_steps, int32_t adapt_window, int32_t thin, double* samples_out,
+             double* loglik_out, void* stream) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    if (n_steps < 0 || adapt_window < 0 || thin < 1) return fail(MEMS_E_INVALID, "bad n_steps/adapt_window/thin");
+    if (n_steps == 0) return MEMS_OK;
+    MemsRunArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.n_steps = n_steps; ra.adapt_window = adapt_window; ra.thin = thin;
+    ra.samples_out = samples_out; ra.loglik_out = loglik_out;
+    return run_common(h, ra, stream);
+}
+
+int mems_run_explicit(mems_handle_t h, int32_t n_steps, int32_t adapt_window, const double* xi, const double* log_u,
+                      double* samples_out, double* loglik_prop_out, uint8_t* decisions_out, void* stream) {
+    if (!h || !xi || !log_u) return fail(MEMS_E_INVALID, "null argument");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    if (n_steps < 0 || adapt_window < 0) return fail(MEMS_E_INVALID, "bad n_steps/adapt_window");
+    if (n_steps == 0) return MEMS_OK;
+    MemsRunArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.n_steps = n_steps; ra.adapt_window = adapt_window; ra.thin = 1;
+    ra.xi = xi; ra.log_u = log_u;
+    ra.samples_out = samples_out; ra.llprop_out = loglik_prop_out; ra.decisions_out = decisions_out;
+    return run_common(h, ra, stream);
+}
+
+int mems_draw(mems_handle_t h, uint64_t step0, int32_t n_steps, double* xi_out, double* log_u_out, void* stream) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    if (n_steps <= 0) return MEMS_OK;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    MemsLaunchCtx ctx = make_ctx(h, stream);
+    const int e = mems_draw_launch(ctx, step0, n_steps, xi_out, log_u_out);
+    h->launches += 1;
+    if (e != 0) return fail(MEMS_E_CUDA, "draw launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+int mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale, uint32_t* accept_count,
+                   uint64_t* steps_done, void* stream) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.P;
+    if (x) CUDA_TRY(cudaMemcpyAsync(x, h->chains.x, sizeof(double) * P * C, cudaMemcpyDeviceToDevice, st));
+    if (loglik) CUDA_TRY(cudaMemcpyAsync(loglik, h->chains.ll, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (scale) CUDA_TRY(cudaMemcpyAsync(scale, h->chains.scale, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (accept_count)
+        CUDA_TRY(cudaMemcpyAsync(accept_count, h->chains.acc_count, sizeof(unsigned int) * C, cudaMemcpyDeviceToDevice, st));
+    if (steps_done) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        *steps_done = h->steps_done;
+    }
+    return MEMS_OK;
+}
+
+int mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths, const float* const* W,
+                     const float* const* b, const float* X_dev, int64_t n, float* Y_dev, void* stream) {
+    if (!widths || !W || !b || !X_dev || !Y_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (n_layers < 1 || n_layers > 9) return fail(MEMS_E_INVALID, "n_layers=%d outside [1,9]", n_layers);
+    for (int i = 0; i <= n_layers; ++i)
+        if (widths[i] < 1 || widths[i] > MEMS_WIDTH) return fail(MEMS_E_INVALID, "widths[%d]=%d outside [1,%d]", i, widths[i], MEMS_WIDTH);
+    if (n < 0) return fail(MEMS_E_INVALID, "n < 0");
+    if (n == 0) return MEMS_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    float* Wd[9] = {nullptr};
+    float* bd[9] = {nullptr};
+    int rc = MEMS_OK;
+    for (int l = 0; l < n_layers && rc == MEMS_OK; ++l) {
+        const size_t wb = sizeof(float) * widths[l] * widths[l + 1], bb = sizeof(float) * widths[l + 1];
+        if (cudaMalloc(&Wd[l], wb) != cudaSuccess || cudaMalloc(&bd[l], bb) != cudaSuccess ||
+            cudaMemcpyAsync(Wd[l], W[l], wb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(bd[l], b[l], bb, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            rc = fail(MEMS_E_CUDA, "weight upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc == MEMS_OK) {
+        const int e = mems_mlp_forward_launch(n_layers, widths, Wd, bd, X_dev, n, Y_dev, prop.multiProcessorCount, st);
+        if (e != 0) rc = fail(MEMS_E_CUDA, "mlp launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    cudaStreamSynchronize(st);   // weights are temporaries of this call
+    for (int l = 0; l < n_layers; ++l) { cudaFree(Wd[l]); cudaFree(bd[l]); }
+    return rc;
+}
+
+int64_t mems_launch_count(mems_handle_t h) { return h ? h->launches : 0; }
+
+int mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev, const void* b_f16_dev, float* d_out_dev,
+                       void* stream) {
+    if (!a_f16_dev || !b_f16_dev || !d_out_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (variant < 0 || variant > 1) return fail(MEMS_E_INVALID, "variant must be 0 (A in TMEM) or 1 (A in shared memory)");
+    CUDA_TRY(cudaSetDevice(device));
+    const int e = mems_tc_selftest(variant, a_f16_dev, b_f16_dev, d_out_dev, reinterpret_cast<cudaStream_t>(stream));
+    if (e != 0) return fail(MEMS_E_CUDA, "selftest launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+// FP32 check path: the whole MH update on CUDA cores, FP32 FMAs and tanhf, no tensor cores.
+//
+// Purpose: pin kernel <-> oracle parity at ~1e-6 relative on surrogate outputs and make
+// accept/reject decisions comparable bit for bit before (and beside) the tcgen05 path.
+// One thread evaluates one (chain, time point) row of the surrogate
+// (reference: src/InverseProblems/utils.py:30-40 builds exactly these rows).
+#include "mems_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;   // threads per block
+
+struct Fp32Smem {
+    ChainBatch cb;
+    float W1[(MEMS_PMAX + 1) * MEMS_WIDTH];
+    float b1[MEMS_WIDTH];
+    float bh[MEMS_NLAYER_H * MEMS_WIDTH];
+    float w7[MEMS_WIDTH];
+    double Spart[NT];
+    __align__(16) float Wh[MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH];
+    float act[MEMS_WIDTH * NT];   // per-thread activation column, element n at act[n*NT + tid]
+    // followed by: double yobs[T]; float ts[T];
+};
+
+__device__ __forceinline__ void load_constants(Fp32Smem& sm, const MemsProblem& pb, double* s_yobs, float* s_ts) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (MEMS_PMAX + 1) * MEMS_WIDTH; i += NT) sm.W1[i] = pb.W1[i];
+    for (int i = tid; i < MEMS_WIDTH; i += NT) { sm.b1[i] = pb.b1[i]; sm.w7[i] = pb.w7[i]; }
+    for (int i = tid; i < MEMS_NLAYER_H * MEMS_WIDTH; i += NT) sm.bh[i] = pb.bh[i];
+    const float4* src = reinterpret_cast<const float4*>(pb.Wh);
+    float4* dst = reinterpret_cast<float4*>(sm.Wh);
+    for (int i = tid; i < MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH / 4; i += NT) dst[i] = src[i];
+    for (int i = tid; i < pb.T; i += NT) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+}
+
+// One surrogate row: scaled inputs (xs[0..P), ts) -> scalar output, everything in FP32.
+__device__ __forceinline__ float mlp_row(const Fp32Smem& sm, float* a, int P, const float* xs, float ts, float b7) {
+    // layer 1: (P+1) -> 64, matmul first then bias (Keras Dense: matmul + BiasAdd)
+#pragma unroll 8
+    for (int n = 0; n < MEMS_WIDTH; ++n) {
+        float z = xs[0] * sm.W1[n];
+        for (int p = 1; p < P; ++p) z = fmaf(xs[p], sm.W1[p * MEMS_WIDTH + n], z);
+        z = fmaf(ts, sm.W1[P * MEMS_WIDTH + n], z);
+        a[n * NT] = tanhf(z + sm.b1[n]);
+    }
+    // layers 2..6: 64 -> 64
+#pragma unroll 1
+    for (int l = 0; l < MEMS_NLAYER_H; ++l) {
+        const float4* W = reinterpret_cast<const float4*>(sm.Wh + l * MEMS_WIDTH * MEMS_WIDTH);
+        float o[MEMS_WIDTH];
+#pragma unroll
+        for (int n = 0; n < MEMS_WIDTH; ++n) o[n] = 0.0f;
+#pragma unroll 2
+        for (int k = 0; k < MEMS_WIDTH; ++k) {
+            const float av = a[k * NT];
+#pragma unroll
+            for (int q = 0; q < MEMS_WIDTH / 4; ++q) {
+                const float4 w = W[k * (MEMS_WIDTH / 4) + q];   // warp-uniform address: broadcast
+                o[4 * q + 0] = fmaf(av, w.x, o[4 * q + 0]);
+                o[4 * q + 1] = fmaf(av, w.y, o[4 * q + 1]);
+                o[4 * q + 2] = fmaf(av, w.z, o[4 * q + 2]);
+                o[4 * q + 3] = fmaf(av, w.w, o[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < MEMS_WIDTH; ++n) a[n * NT] = tanhf(o[n] + sm.bh[l * MEMS_WIDTH + n]);
+    }
+    // output layer: 64 -> 1, linear
+    float out = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < MEMS_WIDTH; ++k) out = fmaf(a[k * NT], sm.w7[k], out);
+    return out + b7;
+}
+
+// S[j] = sum_t (y_obs[t] - f(xs_j)[t])^2 for the batch; result for chain j lands in Spart[j].
+// y_out (optional) receives the surrogate outputs [chain][T].
+__device__ __forceinline__ void eval_batch(Fp32Smem& sm, const double* s_yobs, const float* s_ts, int P, int T,
+                                           float b7, int nc, int ncv, bool skip_dead, float* y_out, int c0) {
+    const int tid = threadIdx.x;
+    const int j = tid & (nc - 1);
+    const int tslot = tid / nc;
+    const int nts = NT / nc;
+    double Sp = 0.0;
+    if (j < ncv && (!skip_dead || sm.cb.inb[j])) {
+        float xs[MEMS_PMAX];
+        for (int p = 0; p < P; ++p) xs[p] = sm.cb.xs[p][j];
+        float* a = sm.act + tid;
+        for (int t = tslot; t < T; t += nts) {
+            const float out = mlp_row(sm, a, P, xs, s_ts[t], b7);
+            if (y_out) y_out[(size_t)(c0 + j) * T + t] = out;
+            const double r = s_yobs[t] - (double)out;
+            Sp = fma(r, r, Sp);
+        }
+    }
+    sm.Spart[tid] = Sp;
+    __syncthreads();
+    if (tid < nc) {
+        double S = 0.0;
+        for (int k = 0; k < nts; ++k) S += sm.Spart[k * nc + tid];
+        sm.Spart[tid] = S;     // only thread tid reads its own slot afterwards
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
+    const MemsProblem& pb = *pbp;
+    double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(Fp32Smem));
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    load_constants(sm, pb, s_yobs, s_ts);
+    const int P = pb.P, T = pb.T, nc = ra.nc;
+    const float b7 = pb.b7;
+    const int tid = threadIdx.x;
+    const int nbatch = (ch.C + nc - 1) / nc;
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int c0 = batch * nc;
+        const int ncv = min(nc, ch.C - c0);
+        __syncthreads();
+        batch_load(sm.cb, ch, P, c0, tid, ncv);
+        __syncthreads();
+        for (int s = 0; s < ra.n_steps; ++s) {
+            if (tid < ncv) batch_propose(sm.cb, pb, ch, ra, c0, tid, s);
+            __syncthreads();
+            eval_batch(sm, s_yobs, s_ts, P, T, b7, nc, ncv, true, nullptr, c0);
+            if (tid < ncv) batch_finish(sm.cb, pb, ch, ra, c0, tid, s, sm.Spart[tid]);
+            __syncthreads();
+        }
+        batch_store(sm.cb, ch, P, c0, tid, ncv);
+    }
+}
+
+__global__ void __launch_bounds__(NT, 1)
+fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict__ x, int n, int nc,
+                    float* y_out, double* ll_out, int apply_prior) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
+    const MemsProblem& pb = *pbp;
+    double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(Fp32Smem));
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    load_constants(sm, pb, s_yobs, s_ts);
+    const int P = pb.P, T = pb.T;
+    const int tid = threadIdx.x;
+    const int nbatch = (n + nc - 1) / nc;
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int c0 = batch * nc;
+        const int ncv = min(nc, n - c0);
+        __syncthreads();
+        if (tid < ncv) {
+            bool inb = true;
+            for (int p = 0; p < P; ++p) {
+                const double v = x[(size_t)p * n + c0 + tid];
+                sm.cb.xs[p][tid] = scale_param(pb, p, v);
+                inb = inb && !(v < pb.low[p]) && !(v > pb.high[p]);
+            }
+            sm.cb.inb[tid] = inb ? 1 : 0;
+        }
+        __syncthreads();
+        eval_batch(sm, s_yobs, s_ts, P, T, pb.b7, nc, ncv, false, y_out, c0);
+        if (tid < ncv && ll_out) {
+            const double ll = pb.neg_half_inv_sigma2 * sm.Spart[tid];
+            ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
+        }
+    }
+}
+
+__global__ void draw_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, unsigned long long step0,
+                            int n_steps, double* xi_out, double* log_u_out) {
+    const MemsProblem& pb = *pbp;
+    const size_t total = (size_t)n_steps * ch.C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i / ch.C), c = (int)(i % ch.C);
+        double xi[MEMS_PMAX], lu;
+        draw_update(pb, ch.seed, ch.chain_id0 + (unsigned long long)c, step0 + (unsigned long long)s, xi, lu);
+        if (xi_out)
+            for (int p = 0; p < pb.P; ++p) xi_out[((size_t)s * pb.P + p) * ch.C + c] = xi[p];
+        if (log_u_out) log_u_out[i] = lu;
+    }
+}
+
+// Generic Dense stack (NN_Model.predict): one thread per input row, widths <= 64.
+constexpr int MLP_NT = 64;
+struct MlpDesc {
+    int n_layers;
+    int widths[10];
+    const float* W[9];
+    const float* b[9];
+};
+
+__global__ void __launch_bounds__(MLP_NT)
+mlp_forward_kernel(MlpDesc d, const float* __restrict__ X, long long n, float* __restrict__ Y) {
+    __shared__ float bufA[MEMS_WIDTH * MLP_NT];
+    __shared__ float bufB[MEMS_WIDTH * MLP_NT];
+    const int tid = threadIdx.x;
+    for (long long row = blockIdx.x * (long long)MLP_NT + tid; row < n; row += (long long)gridDim.x * MLP_NT) {
+        float* in = bufA + tid;
+        float* out = bufB + tid;
+        for (int k = 0; k < d.widths[0]; ++k) in[k * MLP_NT] = X[row * d.widths[0] + k];
+        for (int l = 0; l < d.n_layers; ++l) {
+            const int wi = d.widths[l], wo = d.widths[l + 1];
+            const float* W = d.W[l];
+            const float* b = d.b[l];
+            for (int nn = 0; nn < wo; ++nn) {
+                float acc = 0.0f;
+                for (int k = 0; k < wi; ++k) acc = fmaf(in[k * MLP_NT], __ldg(W + k * wo + nn), acc);
+                acc += __ldg(b + nn);
+                out[nn * MLP_NT] = (l + 1 < d.n_layers) ? tanhf(acc) : acc;
+            }
+            float* t = in; in = out; out = t;
+        }
+        const int wl = d.widths[d.n_layers];
+        for (int k = 0; k < wl; ++k) Y[row * wl + k] = in[k * MLP_NT];
+    }
+}
+
+size_t fp32_smem_bytes(int T) { return sizeof(Fp32Smem) + (size_t)T * (sizeof(double) + sizeof(float)) + 16; }
+
+}  // namespace
+
+int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
+    const size_t smem = fp32_smem_bytes(ctx.pb_host->T);
+    cudaError_t e = cudaFuncSetAttribute(fp32_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
+    const int grid = nbatch < ctx.sm_count ? nbatch : ctx.sm_count;
+    fp32_run_kernel<<<grid, NT, smem, ctx.stream>>>(ctx.pb_dev, ctx.chains, ra);
+    return (int)cudaGetLastError();
+}
+
+int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
+                      int apply_prior) {
+    const size_t smem = fp32_smem_bytes(ctx.pb_host->T);
+    cudaError_t e = cudaFuncSetAttribute(fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    // spread the points over the SMs: smallest power-of-two batch that still fills the grid once
+    int nc = MEMS_NCMAX;
+    while (nc > 1 && (n + nc - 1) / nc < ctx.sm_count) nc >>= 1;
+    const int nbatch = (n + nc - 1) / nc;
+    const int grid = nbatch < 4 * ctx.sm_count ? nbatch : 4 * ctx.sm_count;
+    fp32_forward_kernel<<<grid > 0 ? grid : 1, NT, smem, ctx.stream>>>(ctx.pb_dev, x_dev, n, nc, y_out, ll_out,
+                                                                   apply_prior);
+    return (int)cudaGetLastError();
+}
+
+int mems_draw_launch(const MemsLaunchCtx& ctx, unsigned long long step0, int n_steps, double* xi_out,
+                     double* log_u_out) {
+    const size_t total = (size_t)n_steps * ctx.chains.C;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 8 * ctx.sm_count) grid = 8 * ctx.sm_count;
+    if (grid < 1) grid = 1;
+    draw_kernel<<<grid, 256, 0, ctx.stream>>>(ctx.pb_dev, ctx.chains, step0, n_steps, xi_out, log_u_out);
+    return (int)cudaGetLastError();
+}
+
+int mems_mlp_forward_launch(int n_layers, const int* widths, const float* const* Wd, const float* const* bd,
+                            const float* X, long long n, float* Y, int sm_count, cudaStream_t st) {
+    MlpDesc d;
+    d.n_layers = n_layers;
+    for (int i = 0; i <= n_layers; ++i) d.widths[i] = widths[i];
+    for (int i = 0; i < n_layers; ++i) { d.W[i] = Wd[i]; d.b[i] = bd[i]; }
+    long long blocks = (n + MLP_NT - 1) / MLP_NT;
+    if (blocks > 8LL * sm_count) blocks = 8LL * sm_count;
+    if (blocks < 1) blocks = 1;
+    mlp_forward_kernel<<<(int)blocks, MLP_NT, 0, st>>>(d, X, n, Y);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,746 @@
+// Tensor-core path (sm_100a): one persistent kernel per block of MH updates.
+//
+//   rows      one surrogate row = (chain, time point); a tile is 128 rows = the 128 TMEM lanes
+//   layers    all six tanh layers run as tcgen05.mma kind::f16 GEMMs (M=128, N=64) with FP32
+//             accumulators in TMEM.  FP32 accuracy comes from operand splitting
+//             (SURVEY.md App. C):  a = a_hi + a_lo,  W = W_hi + W_lo  (fp16 each)
+//                 D = a_hi*W_hi + a_lo*W_hi + a_hi*W_lo            (3 MMAs per logical MMA)
+//             Activations never leave the SM: the epilogue reads D with tcgen05.ld, applies tanh,
+//             splits, and writes the next A operand straight back to TMEM (tcgen05.st); A is consumed
+//             from TMEM (".ts" form), weights from shared memory (128B-swizzled, K-major, resident
+//             for the whole run, staged once with a bulk-TMA copy).
+//   bias      added by the tensor core: one extra K=16 MMA of a constant ones-block (shared memory)
+//             against [b_hi; b_mid; b_lo]; 2*log2(e) is folded into weights and biases on the host so the
+//             accumulator is directly the exp2 argument of tanh(z) = 1 - 2/(2^(2z*log2 e) + 1).
+//   layer 1   the (P+1)->64 layer is a K=32 MMA over three-way-split scaled inputs.
+//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns); warps 0..15 are epilogue workers
+//             (slot = warp/4, TMEM lane quarter = warp%4), warp 16 issues every MMA.
+//   tail      64->1 output layer, residual against y_obs, squared-sum reduction in FP64, accept/reject
+//             and chain-state update (mems_common.cuh) all happen in the same kernel.
+//
+// Reference semantics: see mems_common.cuh header (src/InverseProblems/utils.py:30-40 etc.).
+#include <cuda_fp16.h>
+
+#include <cstring>
+
+#include "mems_common.cuh"
+
+namespace {
+
+constexpr int NSLOT = 4;
+constexpr int NWORKER = NSLOT * 128;
+constexpr int NTHREADS = NWORKER + 32;
+constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
+constexpr int BLK_B1 = 0;             // layer-1 B operand
+constexpr int BLK_WHI = 1;            // 5 blocks
+constexpr int BLK_WLO = 6;            // 5 blocks
+constexpr int BLK_BIAS = 11;          // 2 blocks: hidden layer h<4 at k-step h of block 0, h=4 at k-step 0 of block 1
+constexpr int BLK_ONES = 13;          // 2 blocks = 128 rows of [1,1,1,0,...]
+constexpr int NBLK = 15;
+constexpr int WIMG_TAIL = 64 * 4 + 16;                 // w7[64] f32, b7 f32, pad
+constexpr int WIMG_BYTES = NBLK * BLK + WIMG_TAIL;
+constexpr float EXP2_CLAMP = 26.0f;                    // 2^26: tanh == 1 to f32 beyond; keeps 4-products finite
+constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
+
+// instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct TcSmem {
+    __align__(1024) unsigned char wimg[NBLK * BLK];
+    float w7[64];
+    float b7;
+    float pad_[3];
+    ChainBatch cb;
+    double Spart[NWORKER];
+    unsigned long long bar_A[NSLOT];
+    unsigned long long bar_D[NSLOT];
+    unsigned long long bar_w;
+    uint32_t tmem_base;
+    uint32_t err_flag;
+    // followed by: double yobs[T]; float ts[T];
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(void* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);   // .x (low 16 bits) = lo
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// tanh of four accumulator values that already hold 2*log2(e)*z:  t = 1 - 2/(2^y + 1).
+// One MUFU.RCP is shared by the four (products stay < 2^104 thanks to the clamp).
+__device__ __forceinline__ void tanh4(const uint32_t* v, float* t) {
+    float d0 = ex2_approx(fminf(__uint_as_float(v[0]), EXP2_CLAMP)) + 1.0f;
+    float d1 = ex2_approx(fminf(__uint_as_float(v[1]), EXP2_CLAMP)) + 1.0f;
+    float d2 = ex2_approx(fminf(__uint_as_float(v[2]), EXP2_CLAMP)) + 1.0f;
+    float d3 = ex2_approx(fminf(__uint_as_float(v[3]), EXP2_CLAMP)) + 1.0f;
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    const float r = rcp_approx(p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;
+    t[0] = fmaf(r01 * d1, -2.0f, 1.0f);
+    t[1] = fmaf(r01 * d0, -2.0f, 1.0f);
+    t[2] = fmaf(r23 * d3, -2.0f, 1.0f);
+    t[3] = fmaf(r23 * d2, -2.0f, 1.0f);
+}
+
+// 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
+__device__ __forceinline__ void epilogue_split(const uint32_t (&v)[32], uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float t[4];
+        tanh4(&v[4 * g], t);
+        float h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);   // top 11 significant bits: exact in fp16
+            l[i] = t[i] - h[i];
+        }
+        hi2[2 * g] = pack_half2(h[0], h[1]);
+        hi2[2 * g + 1] = pack_half2(h[2], h[3]);
+        lo2[2 * g] = pack_half2(l[0], l[1]);
+        lo2[2 * g + 1] = pack_half2(l[2], l[3]);
+    }
+}
+
+// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights
+__device__ __forceinline__ float epilogue_dot(const uint32_t (&v)[32], const float* w7c, float acc) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float t[4];
+        tanh4(&v[4 * g], t);
+        const float4 w = *reinterpret_cast<const float4*>(w7c + 4 * g);
+        acc = fmaf(t[0], w.x, acc);
+        acc = fmaf(t[1], w.y, acc);
+        acc = fmaf(t[2], w.z, acc);
+        acc = fmaf(t[3], w.w, acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void split3(float v, float& h, float& m, float& l) {
+    h = __half2float(__float2half_rn(v));
+    const float r1 = v - h;
+    m = __half2float(__float2half_rn(r1));
+    l = r1 - m;
+}
+
+// ------------------------------------------------------------------------------------------
+// MMA issue (one thread)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int layer) {
+    if (layer == 0) {
+        const uint64_t b = make_desc(wimg_saddr + BLK_B1 * BLK);
+        umma_ts(d, d + 64, b, 0u);
+        umma_ts(d, d + 64 + 8, b + 2, 1u);
+    } else {
+        const int h = layer - 1;
+        const uint64_t ones = make_desc(wimg_saddr + BLK_ONES * BLK);
+        const uint64_t bias = make_desc(wimg_saddr + (BLK_BIAS + (h >> 2)) * BLK) + 2 * (h & 3);
+        umma_ss(d, ones, bias, 0u);
+        const uint64_t whi = make_desc(wimg_saddr + (BLK_WHI + h) * BLK);
+        const uint64_t wlo = make_desc(wimg_saddr + (BLK_WLO + h) * BLK);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, whi + 2 * ks, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, whi + 2 * ks, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, wlo + 2 * ks, 1u);
+    }
+}
+
+// Serve `units[s]` (tile, layer) requests of every slot, in whatever order their operands arrive.
+__device__ void mma_service(TcSmem& sm, const long long (&units)[NSLOT]) {
+    const uint32_t wimg = smem_u32(sm.wimg);
+    const uint32_t base = sm.tmem_base;
+    long long cnt[NSLOT];
+    uint32_t ph[NSLOT];
+    long long remaining = 0;
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) { cnt[s] = 0; ph[s] = 0; remaining += units[s]; }
+    long long idle_t0 = clock64();
+    while (remaining > 0) {
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+            if (cnt[s] < units[s] && mbar_test(&sm.bar_A[s], ph[s])) {
+                tc_fence_after();
+                issue_layer(wimg, base + s * 128, (int)(cnt[s] % MEMS_HIDDEN));
+                umma_commit(&sm.bar_D[s]);
+                ph[s] ^= 1u;
+                cnt[s] += 1;
+                remaining -= 1;
+                any = true;
+            }
+        }
+        if (any) {
+            idle_t0 = clock64();
+        } else {
+            __nanosleep(20);
+            if (clock64() - idle_t0 > 4000000000LL) __trap();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Worker side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
+// ------------------------------------------------------------------------------------------
+template <int P>
+struct RowInputs {          // the layer-1 A operand of one row, K=32 fp16 = 16 packed words
+    uint32_t a1[16];
+};
+
+// K-slot of (term, input) in the layer-1 operand: terms 0..2 multiply W_hi, 3..4 multiply W_lo
+template <int P>
+__device__ __forceinline__ constexpr int k1_slot(int term, int i) { return term * (P + 1) + i; }
+
+template <int P>
+__device__ __forceinline__ void set_half(uint32_t (&a1)[16], int slot, float v) {
+    const unsigned short hb = __half_as_ushort(__float2half_rn(v));
+    const int w = slot >> 1;
+    if (slot & 1) a1[w] = (a1[w] & 0x0000FFFFu) | ((uint32_t)hb << 16);
+    else a1[w] = (a1[w] & 0xFFFF0000u) | (uint32_t)hb;
+}
+
+template <int P>
+__device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
+    float h, m, l;
+    split3(v, h, m, l);
+    set_half<P>(a1, k1_slot<P>(0, i), h);
+    set_half<P>(a1, k1_slot<P>(1, i), m);
+    set_half<P>(a1, k1_slot<P>(2, i), l);
+    set_half<P>(a1, k1_slot<P>(3, i), h);
+    set_half<P>(a1, k1_slot<P>(4, i), m);
+}
+
+template <int P>
+__device__ __forceinline__ void tc_eval_batch(TcSmem& sm, const double* s_yobs, const float* s_ts, int T, int nc,
+                                              int log2nc, int ncv, bool skip_dead, float* y_out, int c0,
+                                              uint32_t& phaseD) {
+    const int wtid = threadIdx.x;
+    const int warp = wtid >> 5, lane = wtid & 31;
+    const int slot = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const int j = row & (nc - 1);
+    const int sub = row >> log2nc;
+    const int tpt = 128 >> log2nc;                    // time points per tile
+    const int n_tiles = (T + tpt - 1) / tpt;
+    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
+    const bool chain_live = (j < ncv) && (!skip_dead || sm.cb.inb[j]);
+
+    uint32_t a1[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a1[i] = 0u;
+#pragma unroll
+    for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? sm.cb.xs[p][j] : 0.0f);
+    set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);           // ones that pick up b_hi, b_mid, b_lo
+    set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
+    set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
+
+    double Sp = 0.0;
+    for (int tile = slot; tile < n_tiles; tile += NSLOT) {
+        const int t = tile * tpt + sub;
+        const bool live = chain_live && (t < T);
+        put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
+        tmem_st16(tD + 64, a1);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&sm.bar_A[slot]);
+
+        float out = 0.0f;
+#pragma unroll 1
+        for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+            mbar_wait(&sm.bar_D[slot], phaseD);
+            phaseD ^= 1u;
+            tc_fence_after();
+            if (layer < MEMS_HIDDEN - 1) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32], hi2[16], lo2[16];
+                    tmem_ld32(tD + 32 * c, v);
+                    tc_wait_ld();
+                    epilogue_split(v, hi2, lo2);
+                    tmem_st16(tD + 64 + 16 * c, hi2);
+                    tmem_st16(tD + 96 + 16 * c, lo2);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(&sm.bar_A[slot]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tD + 32 * c, v);
+                    tc_wait_ld();
+                    out = epilogue_dot(v, sm.w7 + 32 * c, out);
+                }
+                // the slot's D and A regions are free again: every read of this tile has completed
+                tc_fence_before();
+            }
+        }
+        out += sm.b7;
+        if (live) {
+            if (y_out) y_out[(size_t)(c0 + j) * T + t] = out;
+            const double r = s_yobs[t] - (double)out;
+            Sp = fma(r, r, Sp);
+        }
+    }
+    sm.Spart[wtid] = Sp;
+    named_bar_sync(1, NWORKER);
+    if (wtid < nc) {
+        // fixed summation order: slot-major, then time sub-row
+        double S = 0.0;
+        for (int s = 0; s < NSLOT; ++s)
+            for (int u = 0; u < tpt; ++u) S += sm.Spart[s * 128 + u * nc + wtid];
+        sm.Spart[wtid] = S;   // thread wtid only ever reads slots {s*128 + u*nc + wtid}: no cross-thread hazard
+    }
+}
+
+__device__ __forceinline__ long long tiles_of_slot(int n_tiles, int s) {
+    return (n_tiles > s) ? (long long)((n_tiles - s + NSLOT - 1) / NSLOT) : 0;
+}
+
+__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
+
+// Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
+__device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, double* s_yobs, float* s_ts) {
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.bar_A[s], 128); mbar_init(&sm.bar_D[s], 1); }
+        mbar_init(&sm.bar_w, 1);
+        sm.err_flag = 0;
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp == NWORKER / 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem_base)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if ((tid & 31) == 0) {
+            mbar_arrive_expect_tx(&sm.bar_w, (uint32_t)WIMG_BYTES);
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(pb.wimg);
+            for (int b = 0; b < NBLK; ++b) bulk_g2s(sm.wimg + b * BLK, src + (size_t)b * BLK, BLK, &sm.bar_w);
+            bulk_g2s(sm.w7, src + (size_t)NBLK * BLK, WIMG_TAIL, &sm.bar_w);
+        }
+    }
+    for (int i = tid; i < pb.T; i += NTHREADS) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(&sm.bar_w, 0);
+}
+
+__device__ __forceinline__ void tc_epilogue_free(TcSmem& sm) {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == NWORKER / 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+    const MemsProblem& pb = *pbp;
+    double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    tc_prologue(sm, pb, s_yobs, s_ts);
+
+    const int T = pb.T, nc = ra.nc, log2nc = ilog2(ra.nc);
+    const int tid = threadIdx.x;
+    const int nbatch = (ch.C + nc - 1) / nc;
+    const int my_batches = (nbatch > (int)blockIdx.x) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int tpt = 128 >> log2nc;
+    const int n_tiles = (T + tpt - 1) / tpt;
+
+    if (tid >= NWORKER) {
+        if ((tid & 31) == 0) {
+            long long units[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s)
+                units[s] = (long long)my_batches * ra.n_steps * tiles_of_slot(n_tiles, s) * MEMS_HIDDEN;
+            mma_service(sm, units);
+        }
+        __syncwarp();
+    } else {
+        uint32_t phaseD = 0;
+        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+            const int c0 = batch * nc;
+            const int ncv = min(nc, ch.C - c0);
+            named_bar_sync(1, NWORKER);
+            batch_load(sm.cb, ch, P, c0, tid, ncv);
+            for (int s = 0; s < ra.n_steps; ++s) {
+                if (tid < ncv) batch_propose(sm.cb, pb, ch, ra, c0, tid, s);
+                named_bar_sync(1, NWORKER);
+                tc_eval_batch<P>(sm, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phaseD);
+                if (tid < ncv) batch_finish(sm.cb, pb, ch, ra, c0, tid, s, sm.Spart[tid]);
+            }
+            batch_store(sm.cb, ch, P, c0, tid, ncv);
+        }
+    }
+    tc_epilogue_free(sm);
+}
+
+template <int P>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict__ x, int n, int nc, float* y_out,
+                  double* ll_out, int apply_prior) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+    const MemsProblem& pb = *pbp;
+    double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    tc_prologue(sm, pb, s_yobs, s_ts);
+
+    const int T = pb.T, log2nc = ilog2(nc);
+    const int tid = threadIdx.x;
+    const int nbatch = (n + nc - 1) / nc;
+    const int my_batches = (nbatch > (int)blockIdx.x) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int tpt = 128 >> log2nc;
+    const int n_tiles = (T + tpt - 1) / tpt;
+
+    if (tid >= NWORKER) {
+        if ((tid & 31) == 0) {
+            long long units[NSLOT];
+#pragma unroll
+            for (int s = 0; s < NSLOT; ++s) units[s] = (long long)my_batches * tiles_of_slot(n_tiles, s) * MEMS_HIDDEN;
+            mma_service(sm, units);
+        }
+        __syncwarp();
+    } else {
+        uint32_t phaseD = 0;
+        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+            const int c0 = batch * nc;
+            const int ncv = min(nc, n - c0);
+            named_bar_sync(1, NWORKER);
+            if (tid < ncv) {
+                bool inb = true;
+                for (int p = 0; p < P; ++p) {
+                    const double v = x[(size_t)p * n + c0 + tid];
+                    sm.cb.xs[p][tid] = scale_param(pb, p, v);
+                    inb = inb && !(v < pb.low[p]) && !(v > pb.high[p]);
+                }
+                sm.cb.inb[tid] = inb ? 1 : 0;
+            }
+            named_bar_sync(1, NWORKER);
+            tc_eval_batch<P>(sm, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phaseD);
+            if (tid < ncv && ll_out) {
+                const double ll = pb.neg_half_inv_sigma2 * sm.Spart[tid];
+                ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
+            }
+        }
+    }
+    tc_epilogue_free(sm);
+}
+
+// ------------------------------------------------------------------------------------------
+// Self-test: D[128][64] = A[128][64] * B[64][64]^T through the same descriptors / TMEM paths.
+//   variant 0: A from TMEM (tcgen05.st packed fp16), variant 1: A from shared memory (SS form).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sw128_offset(int row, int k) {   // byte offset of element (row, k) in a block
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+}
+
+__global__ void __launch_bounds__(160, 1)
+umma_selftest_kernel(int variant, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sB = smem_raw;                    // 8 KB
+    unsigned char* sA = smem_raw + BLK;              // 16 KB
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 3 * BLK);
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(smem_raw + 3 * BLK + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    for (int i = tid; i < 64 * 64; i += blockDim.x) {
+        const int n = i >> 6, k = i & 63;
+        *reinterpret_cast<__half*>(sB + sw128_offset(n, k)) = B[i];
+    }
+    for (int i = tid; i < 128 * 64; i += blockDim.x) {
+        const int m = i >> 6, k = i & 63;
+        *reinterpret_cast<__half*>(sA + sw128_offset(m, k)) = A[i];
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = *tbase;
+    if (warp < 4) {
+        const uint32_t tl = base + ((uint32_t)(warp * 32) << 16);
+        if (variant == 0) {
+            const int m = warp * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int k = 32 * c + 2 * i;
+                    w[i] = (uint32_t)__half_as_ushort(A[m * 64 + k]) | ((uint32_t)__half_as_ushort(A[m * 64 + k + 1]) << 16);
+                }
+                tmem_st16(tl + 64 + 16 * c, w);
+            }
+            tc_wait_st();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+        tc_fence_after();
+        const uint64_t b = make_desc(smem_u32(sB));
+        const uint64_t a = make_desc(smem_u32(sA));
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            if (variant == 0) umma_ts(base, base + 64 + 8 * ks, b + 2 * ks, ks > 0 ? 1u : 0u);
+            else umma_ss(base, a + 2 * ks, b + 2 * ks, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar);
+    }
+    if (warp < 4) {
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        const uint32_t tl = base + ((uint32_t)(warp * 32) << 16);
+        const int m = warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tl + 32 * c, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) D[m * 64 + 32 * c + i] = __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(128) : "memory");
+    }
+}
+
+size_t tc_smem_bytes(int T) { return sizeof(TcSmem) + (size_t)T * (sizeof(double) + sizeof(float)) + 16; }
+
+// host-side fp16 helpers (round to nearest even through the CUDA host implementation)
+inline unsigned short h_bits(double v) {
+    const __half h = __float2half_rn((float)v);
+    unsigned short b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+inline double h_val(double v) { return (double)__half2float(__float2half_rn((float)v)); }
+
+inline void put(unsigned char* img, int blk, int row, int k, double v) {
+    const size_t off = (size_t)blk * BLK + (size_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
+    const unsigned short b = h_bits(v);
+    memcpy(img + off, &b, 2);
+}
+
+#define MEMS_LAUNCH_P(KERNEL, Pv, grid, smem, st, ...)                                                         \
+    do {                                                                                                      \
+        cudaError_t e_;                                                                                       \
+        switch (Pv) {                                                                                         \
+            case 1: e_ = cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+                if (e_ == cudaSuccess) KERNEL<1><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
+            case 2: e_ = cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+                if (e_ == cudaSuccess) KERNEL<2><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
+            case 3: e_ = cudaFuncSetAttribute(KERNEL<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+                if (e_ == cudaSuccess) KERNEL<3><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
+            default: e_ = cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
+                if (e_ == cudaSuccess) KERNEL<4><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
+        }                                                                                                     \
+        if (e_ != cudaSuccess) return (int)e_;                                                                \
+        return (int)cudaGetLastError();                                                                       \
+    } while (0)
+
+}  // namespace
+
+size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
+
+// Build the shared-memory image: 128B-swizzled fp16 operand blocks + the FP32 output layer.
+void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
+    unsigned char* img = static_cast<unsigned char*>(host_img);
+    memset(img, 0, WIMG_BYTES);
+    const int P = pb.P, nin = P + 1;
+    // layer 1: rows n (output neuron), K slots as in k1_slot(): terms 0..2 carry W_hi, 3..4 W_lo
+    for (int n = 0; n < MEMS_WIDTH; ++n) {
+        for (int i = 0; i < nin; ++i) {
+            const double w = C2 * (double)pb.W1[i * MEMS_WIDTH + n];
+            const double whi = h_val(w), wlo = h_val(w - whi);
+            put(img, BLK_B1, n, 0 * nin + i, whi);
+            put(img, BLK_B1, n, 1 * nin + i, whi);
+            put(img, BLK_B1, n, 2 * nin + i, whi);
+            put(img, BLK_B1, n, 3 * nin + i, wlo);
+            put(img, BLK_B1, n, 4 * nin + i, wlo);
+        }
+        const double b = C2 * (double)pb.b1[n];
+        const double bh = h_val(b), bm = h_val(b - bh), bl = h_val(b - bh - bm);
+        put(img, BLK_B1, n, 5 * nin + 0, bh);
+        put(img, BLK_B1, n, 5 * nin + 1, bm);
+        put(img, BLK_B1, n, 5 * nin + 2, bl);
+    }
+    // hidden layers: B[n][k] = 2log2e * W[k][n]
+    for (int h = 0; h < MEMS_NLAYER_H; ++h) {
+        for (int n = 0; n < MEMS_WIDTH; ++n) {
+            for (int k = 0; k < MEMS_WIDTH; ++k) {
+                const double w = C2 * (double)pb.Wh[(h * MEMS_WIDTH + k) * MEMS_WIDTH + n];
+                const double whi = h_val(w);
+                put(img, BLK_WHI + h, n, k, whi);
+                put(img, BLK_WLO + h, n, k, w - whi);
+            }
+            const double b = C2 * (double)pb.bh[h * MEMS_WIDTH + n];
+            const double bh = h_val(b), bm = h_val(b - bh), bl = h_val(b - bh - bm);
+            const int blk = BLK_BIAS + (h >> 2), k0 = 16 * (h & 3);
+            put(img, blk, n, k0 + 0, bh);
+            put(img, blk, n, k0 + 1, bm);
+            put(img, blk, n, k0 + 2, bl);
+        }
+    }
+    for (int m = 0; m < 128; ++m)
+        for (int k = 0; k < 3; ++k) put(img, BLK_ONES + (m >> 6), m & 63, k, 1.0);
+    float* tail = reinterpret_cast<float*>(img + (size_t)NBLK * BLK);
+    for (int k = 0; k < MEMS_WIDTH; ++k) tail[k] = pb.w7[k];
+    tail[MEMS_WIDTH] = pb.b7;
+}
+
+int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
+    const size_t smem = tc_smem_bytes(ctx.pb_host->T);
+    const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
+    const int grid = nbatch < ctx.sm_count ? nbatch : ctx.sm_count;
+    MEMS_LAUNCH_P(tc_run_kernel, ctx.pb_host->P, grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
+}
+
+int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
+                    int apply_prior) {
+    const size_t smem = tc_smem_bytes(ctx.pb_host->T);
+    int nc = MEMS_NCMAX;
+    while (nc > 1 && (n + nc - 1) / nc < ctx.sm_count) nc >>= 1;
+    const int nbatch = (n + nc - 1) / nc;
+    const int grid = nbatch < ctx.sm_count ? nbatch : ctx.sm_count;
+    MEMS_LAUNCH_P(tc_forward_kernel, ctx.pb_host->P, (grid > 0 ? grid : 1), smem, ctx.stream, ctx.pb_dev, x_dev, n, nc,
+                  y_out, ll_out, apply_prior);
+}
+
+int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st) {
+    const size_t smem = 3 * BLK + 64;
+    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    umma_selftest_kernel<<<1, 160, smem, st>>>(variant, static_cast<const __half*>(a_f16),
+                                               static_cast<const __half*>(b_f16), d_out);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,350 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Tolerances (north_star): surrogate outputs / log-likelihoods 1e-5 relative on the FP32 check path,
+1e-3 relative under tensor-core math; accept/reject decisions bit-exact at the decision stage, flips
+allowed only inside a stated near-tie band (|log u - min(0, dl)| <= band) and counted.
+"""
+import numpy as np
+import pytest
+
+import helpers
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+PATHS = [0, 1]            # MEMS_PATH_FP32, MEMS_PATH_TC
+PATH_IDS = ["fp32", "tc"]
+OUT_RTOL = {0: 1e-5, 1: 1e-5}          # on outputs of magnitude ~65 fF
+LL_RTOL = {0: 1e-5, 1: 1e-3}
+BAND = {0: 2e-3, 1: 2e-2}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(lib_built):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    assert torch.cuda.get_device_capability(0)[0] == 10, "sm_100 device required"
+
+
+def _points(pb, n, seed):
+    rng = np.random.default_rng(seed)
+    P = len(pb["low"])
+    box = rng.uniform(pb["low"], pb["high"], size=(n // 2, P))
+    L = np.linalg.cholesky(pb["cov"] * pb["sigma2"])
+    post = pb["x_opts"][0] + rng.standard_normal((n - n // 2, P)) @ L.T
+    return np.vstack([box, post])
+
+
+# ----------------------------------------------------------------------------- tensor-core plumbing
+@pytest.mark.parametrize("variant", [0, 1], ids=["A_in_TMEM", "A_in_SMEM"])
+def test_umma_selftest(variant):
+    import ctypes
+    from mcmc_mems_b200 import _lib
+    g = torch.Generator(device="cpu").manual_seed(variant)
+    A = (torch.randn(128, 64, generator=g)).half().cuda()
+    B = (torch.randn(64, 64, generator=g)).half().cuda()
+    D = torch.full((128, 64), float("nan"), device="cuda")
+    rc = _lib.lib().mems_selftest_umma(0, variant, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+                                       ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "mems_selftest_umma")
+    torch.cuda.synchronize()
+    want = A.float() @ B.float().t()
+    err = (D - want).abs().max().item()
+    assert err < 2e-4, f"UMMA self-test variant {variant}: max abs err {err}"
+
+
+# ----------------------------------------------------------------------------- forward / log-likelihood
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("name", ["geometric", "qfactor"])
+def test_forward_parity(name, path):
+    from oracle import batched_forward
+    pb = helpers.load_problem(name)
+    X = _points(pb, 600, 1)
+    eng = helpers.engine(pb, 1, path)
+    y, ll = eng.forward(X)
+    torch.cuda.synchronize()
+    y, ll = y.cpu().numpy(), ll.cpu().numpy()
+    want = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], X)
+    want64 = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], X, np.float64)
+    assert y.shape == want.shape and y.dtype == np.float32
+    rel = np.max(np.abs(y - want64) / np.maximum(1.0, np.abs(want64)))
+    assert rel < OUT_RTOL[path], f"surrogate outputs rel err {rel}"
+    ll_want = helpers.loglik_core(pb, want)
+    ll_rel = np.max(np.abs(ll - ll_want) / np.maximum(1.0, np.abs(ll_want)))
+    assert ll_rel < LL_RTOL[path], f"log-likelihood rel err {ll_rel}"
+    # what accept/reject consumes: differences between neighbouring posterior points (must be << 1)
+    post = slice(300, 600)
+    dd = np.diff(ll[post]) - np.diff(helpers.loglik_core(pb, want64)[post])
+    assert np.sqrt(np.mean(dd ** 2)) < 0.02, f"delta-loglik error rms {np.sqrt(np.mean(dd ** 2))}"
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_forward_long_trace_T1000(path):
+    """Z-accelerometer configuration: same surrogate, time grid resampled to 1000 points."""
+    from oracle import batched_forward
+    pb = helpers.load_problem("geometric")
+    pb["time"] = np.linspace(0.0, 1.49e-3, 1000)
+    X = _points(pb, 70, 2)
+    f_true = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], pb["x_true"][None])[0]
+    pb["y_obs"] = f_true + np.sqrt(pb["sigma2"]) * np.random.default_rng(0).standard_normal(1000)
+    eng = helpers.engine(pb, 1, path)
+    y, ll = eng.forward(X)
+    want = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], X, np.float64)
+    rel = np.max(np.abs(y.cpu().numpy() - want) / np.maximum(1.0, np.abs(want)))
+    assert rel < OUT_RTOL[path]
+    ll_want = helpers.loglik_core(pb, want)
+    assert np.max(np.abs(ll.cpu().numpy() - ll_want) / np.maximum(1.0, np.abs(ll_want))) < LL_RTOL[path]
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_forward_edge_sizes(path):
+    pb = helpers.load_problem("geometric")
+    eng = helpers.engine(pb, 1, path)
+    y, ll = eng.forward(np.zeros((0, 3)))
+    assert y.shape == (0, 150) and ll.shape == (0,)
+    f = helpers.oracle_forward(pb)
+    for n in (1, 2, 129, 257):                      # ragged: not multiples of any batch size
+        X = _points(pb, max(n, 2), n)[:n]
+        y, _ = eng.forward(X)
+        got = y.cpu().numpy()
+        for i in (0, n - 1):
+            assert np.max(np.abs(got[i] - f(X[i]))) < 1e-3
+    eng.close()
+
+
+def test_generic_predict_matches_tf_known_answer():
+    """K1 on the GPU: NN_Model.predict on the FFT surrogate equals the TF float32 rows printed in
+    tests/Xaccelerometer_quality_factor/surrogate_fft.ipynb cell 11."""
+    import os
+    from mcmc_mems_b200 import NN_Model
+    d = np.load(os.path.join(helpers.GOLDEN, "k1_fft.npz"))
+    m = NN_Model()
+    m.set_layers(helpers.layers_of(d))
+    pred = m.predict(d["X_test_scaled"])
+    assert pred.shape == (10, 15) and pred.dtype == np.float32
+    assert np.max(np.abs(pred - d["tf_pred"])) < 1e-3
+    assert np.allclose(m.model(d["X_test_scaled"]).numpy(), pred)
+
+
+# ----------------------------------------------------------------------------- MH updates, explicit randomness
+def _explicit_inputs(pb, C, S, seed, spread=0.05):
+    rng = np.random.default_rng(seed)
+    P = len(pb["low"])
+    L = np.linalg.cholesky(pb["cov"])
+    x0 = pb["x_opts"][0][None, :] + spread * rng.standard_normal((C, P)) @ L.T
+    xi = rng.standard_normal((S, C, P)) @ L.T
+    log_u = np.log(rng.random((S, C)))
+    return x0, xi, log_u
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("name,C,cpb", [("geometric", 96, 0), ("geometric", 5, 1), ("qfactor", 200, 128), ("geometric", 40, 16)])
+def test_explicit_run_parity(name, C, cpb, path):
+    pb = helpers.load_problem(name)
+    S = 24
+    x0, xi, log_u = _explicit_inputs(pb, C, S, 3)
+    eng = helpers.engine(pb, C, path, chains_per_block=cpb)
+    eng.init_chains(x0, scale0=0.12)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u)
+    torch.cuda.synchronize()
+    res = helpers.check_explicit_run(pb, x0, 0.12, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(),
+                                     dec.cpu().numpy(), band=BAND[path])
+    assert res["flips"] == 0, res                       # no decision differs outside the near-tie band
+    assert res["near_ties"] <= max(1, C * S // 200), res
+    assert res["max_ll_err"] < LL_RTOL[path], res
+    assert res["state_err"] == 0.0, res                 # states are bit-exact given the decisions
+    st = eng.state()
+    assert st["steps_done"] == S
+    assert np.array_equal(st["accept_count"].cpu().numpy(), dec.cpu().numpy().sum(axis=0))
+    assert np.array_equal(st["x"].cpu().numpy(), smp[-1].cpu().numpy())
+    assert 0.05 < dec.float().mean().item() < 0.9
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_out_of_box_proposals_and_starts(path):
+    pb = helpers.load_problem("geometric")
+    C, S = 32, 6
+    x0, xi, log_u = _explicit_inputs(pb, C, S, 4)
+    x0[:8, 0] = 0.7                                      # start outside the prior box: logd = -inf
+    xi[0, 8:16, 2] = 1e3                                 # proposals far outside: always rejected
+    eng = helpers.engine(pb, C, path)
+    eng.init_chains(x0, scale0=0.1)
+    assert np.all(np.isneginf(eng.state()["loglik"].cpu().numpy()[:8]))
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u)
+    dec, llp = dec.cpu().numpy(), llp.cpu().numpy()
+    assert np.all(dec[0, 8:16] == 0) and np.all(np.isneginf(llp[0, 8:16]))
+    res = helpers.check_explicit_run(pb, x0, 0.1, xi, log_u, smp.cpu().numpy(), llp, dec, band=BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0, res
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_adaptation_follows_cuqi_rule(path):
+    """Scale trajectory recomputed from the kernel's own decisions with the CUQIpy 0.8.0 formula."""
+    pb = helpers.load_problem("geometric")
+    C, S, Na = 48, 60, 10
+    x0, xi, log_u = _explicit_inputs(pb, C, S, 5)
+    eng = helpers.engine(pb, C, path)
+    eng.init_chains(x0, scale0=0.1)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u, adapt_window=Na)
+    dec = dec.cpu().numpy().astype(np.float64)
+    acc = np.vstack([np.ones((1, C)), dec])              # acc[0] = 1
+    lam = np.full(C, 0.1)
+    scale_steps = np.empty((S, C))
+    scale = lam.copy()
+    i = idx = 0
+    for s in range(S):
+        scale_steps[s] = scale
+        if (s + 1) % Na == 0:
+            hat = acc[idx:idx + Na].mean(axis=0)
+            lam = np.exp(np.log(lam) + (hat - 0.234) / np.sqrt(i + 1))
+            scale = np.minimum(lam, 1.0)
+            i += 1
+            idx += Na
+    got = eng.state()["scale"].cpu().numpy()
+    assert np.allclose(got, scale, rtol=1e-13, atol=0)
+    assert len(np.unique(np.round(got, 12))) > 3          # chains adapted differently
+    res = helpers.check_explicit_run(pb, x0, scale_steps, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(),
+                                     dec.astype(np.uint8), band=BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0, res
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- Philox stream
+def test_philox_stream_matches_numpy_philox():
+    from oracle import philox4x32_10
+    pb = helpers.load_problem("geometric")
+    C, S, seed, cid0 = 50, 7, 0x5EED0000ABCD, 1000
+    eng = helpers.engine(pb, C, 0)
+    eng.init_chains(np.tile(pb["x_opts"][0], (C, 1)), seed=seed, chain_id0=cid0)
+    xi, lu = eng.draw(3, S)
+    xi, lu = xi.cpu().numpy(), lu.cpu().numpy()
+    ctr = np.zeros((S, C, 4), np.uint32)
+    ctr[:, :, 0] = cid0 + np.arange(C)[None, :]
+    ctr[:, :, 2] = 3 + np.arange(S)[:, None]
+    key = np.array([seed & 0xFFFFFFFF, seed >> 32], np.uint32)
+    ctr_u = ctr.copy()
+    ctr_u[:, :, 3] |= np.uint32(1 << 24)
+    u = philox4x32_10(ctr_u, key)[..., 0].astype(np.float64)
+    assert np.allclose(lu, np.log((u + 1.0) * 2.0 ** -32), rtol=1e-15, atol=1e-15)
+    n = philox4x32_10(ctr, key)
+    u1 = (n[..., 0].astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -32)
+    u2 = (n[..., 1].astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -32)
+    z0 = np.sqrt(-2 * np.log(u1.astype(np.float64))) * np.cos(2 * np.pi * u2.astype(np.float64))
+    L = np.linalg.cholesky(pb["cov"])
+    assert np.allclose(xi[:, 0, :], L[0, 0] * z0, rtol=1e-5, atol=1e-7)
+    eng.close()
+
+
+def test_philox_proposals_have_the_requested_covariance():
+    pb = helpers.load_problem("geometric")
+    C = 4096
+    eng = helpers.engine(pb, C, 0)
+    eng.init_chains(np.tile(pb["x_opts"][0], (C, 1)), seed=7)
+    xi, lu = eng.draw(0, 50)
+    x = xi.permute(0, 2, 1).reshape(-1, 3).cpu().numpy()
+    cov = np.cov(x.T)
+    assert np.allclose(cov, pb["cov"], rtol=0.03, atol=1e-6)
+    assert np.all(np.abs(x.mean(axis=0)) < 4 * np.sqrt(np.diag(pb["cov"]) / len(x)))
+    u = np.exp(lu.cpu().numpy().ravel())
+    assert abs(u.mean() - 0.5) < 0.005 and u.min() > 0 and u.max() <= 1.0
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_philox_run_equals_explicit_replay_and_is_shard_invariant(path):
+    pb = helpers.load_problem("geometric")
+    C, S = 64, 30
+    x0, _, _ = _explicit_inputs(pb, C, S, 6)
+    a = helpers.engine(pb, C, path)
+    a.init_chains(x0, scale0=0.13, seed=11)
+    xi, lu = a.draw(0, S)
+    smp_a, ll_a = a.run(S, adapt_window=10, keep_loglik=True)
+    b = helpers.engine(pb, C, path)
+    b.init_chains(x0, scale0=0.13, seed=11)
+    smp_b, _, _ = b.run_explicit(xi, lu, adapt_window=10)
+    assert torch.equal(smp_a, smp_b)
+    # two shards with global chain ids == one engine (results do not depend on the GPU count)
+    h = C // 2
+    outs = []
+    for r in range(2):
+        e = helpers.engine(pb, h, path)
+        e.init_chains(x0[r * h:(r + 1) * h], scale0=0.13, seed=11, chain_id0=r * h)
+        outs.append(e.run(S, adapt_window=10)[0])
+        e.close()
+    assert torch.equal(torch.cat(outs, dim=2), smp_a)
+    # thinning keeps every k-th state; calls compose
+    c = helpers.engine(pb, C, path)
+    c.init_chains(x0, scale0=0.13, seed=11)
+    s1, _ = c.run(20, adapt_window=10, thin=5)
+    s2, _ = c.run(10, adapt_window=10, thin=5)
+    assert torch.equal(torch.cat([s1, s2]), smp_a[4::5])
+    for e in (a, b, c):
+        e.close()
+
+
+# ----------------------------------------------------------------------------- statistics (K3 / K4 / K5)
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_adaptive_mh_statistics_match_notebook(path):
+    """256 chains x 6000 adaptive updates (the notebook runs 5): acceptance 0.269-0.280, scale
+    0.125-0.131 printed at identification.ipynb:254-278; spread vs samples/sample_10.npy."""
+    from mcmc_mems_b200 import diagnostics
+    pb = helpers.load_problem("geometric")
+    C, N = 256, 6000
+    x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
+    eng = helpers.engine(pb, C, path)
+    eng.init_chains(x0, scale0=0.1, seed=2024)
+    smp, _ = eng.run(N - 1, adapt_window=600)
+    st = eng.state()
+    acc = (st["accept_count"].cpu().numpy() + 1) / N
+    scale = st["scale"].cpu().numpy()
+    assert 0.255 < acc.mean() < 0.29, acc.mean()
+    assert 0.118 < np.median(scale) < 0.138, np.median(scale)
+    S = smp.cpu().numpy()[1000::5]                       # burnthin(1000, 5)
+    pooled = S.transpose(1, 0, 2).reshape(3, -1)
+    g = helpers.pins()["geometric_sample_10"]
+    assert np.all(np.abs(pooled.std(axis=1) / np.array(g["std"]) - 1.0) < 0.2)
+    # oracle posterior on the same y_obs: means within MC error
+    from oracle import mh_sample_adapt
+    L = np.linalg.cholesky(pb["cov"])
+    ref = np.hstack([mh_sample_adapt(helpers.oracle_logd(pb), pb["x_opts"][k], N, 0, rng=np.random.default_rng(k), chol=L)[0][:, 1000::5]
+                     for k in range(3)])
+    se = ref.std(axis=1) / np.sqrt(150)                  # ~ESS of 3 thinned oracle chains
+    assert np.all(np.abs(pooled.mean(axis=1) - ref.mean(axis=1)) < 5 * se)
+    assert np.all(np.abs(pooled.std(axis=1) / ref.std(axis=1) - 1.0) < 0.15)
+    rhat = [diagnostics.rhat_rank(S[:, j, :16].T) for j in range(3)]
+    assert max(rhat) < 1.02, rhat
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- drop-in API
+def test_reference_shaped_api_end_to_end():
+    """The notebook cells (identification.ipynb cells 8-14) with the look-alike objects."""
+    from mcmc_mems_b200 import (Continuous1D, Discrete, FixtureProcessor, Gaussian, JointDistribution, MH, Model,
+                                NN_Model, Uniform, create_forward_model_function, least_squares_optimization)
+    pb = helpers.load_problem("geometric")
+    dp = FixtureProcessor(pb["time"], pb["scaler_mean"], pb["scaler_scale"])
+    nn = NN_Model()
+    nn.set_layers(pb["layers"])
+    fwd = create_forward_model_function(dp, nn)
+    y = fwd(pb["x_true"])
+    assert y.shape == (150,) and y.dtype == np.float32
+    assert np.max(np.abs(y - helpers.oracle_forward(pb)(pb["x_true"]))) < 1e-3
+    model = Model(forward=fwd, range_geometry=Continuous1D(150), domain_geometry=Discrete(["Overetch", "Offset", "Thickness"]))
+    xd = Uniform(low=pb["low"], high=pb["high"])
+    yd = Gaussian(mean=model(xd), cov=pb["sigma2"] * np.eye(150))
+    post = JointDistribution(xd, yd)(y_distribution=pb["y_obs"])
+    x_opt, cov = least_squares_optimization(pb["y_obs"], fwd, pb["starts"][0], (pb["low"], pb["high"]))
+    assert np.allclose(x_opt, pb["x_opts"][0], rtol=2e-3)
+    assert np.allclose(np.sqrt(np.diag(cov)), np.sqrt(np.diag(pb["cov"])), rtol=0.1)
+    prop = Gaussian(mean=np.zeros(3), cov=pb["cov"])
+    s = MH(target=post, proposal=prop, x0=x_opt, seed=1).sample_adapt(2000, 0)
+    assert s.samples.shape == (3, 2000) and np.array_equal(s.samples[:, 0], x_opt)
+    assert 0.2 < s.acc_rate < 0.4 and s.loglike_eval.shape == (2000,)
+    assert s.loglike_eval[0] == pytest.approx(helpers.oracle_logd(pb)(x_opt), abs=0.05)
+    b = s.burnthin(500, 5)
+    assert b.samples.shape == (3, 300) and np.all(b.compute_ess() > 10)
+    many = MH(target=post, proposal=prop, x0=np.tile(x_opt, (16, 1)), seed=2).sample_adapt(1500, 100)
+    assert many.samples.shape == (16, 3, 1500) and np.all(many.compute_rhat() < 1.2)

@@ -1,0 +1,160 @@
+"""CPU tests: the oracle against every pin the reference holds for this path."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import (batched_forward, cwmh_sample, da_sample, decide, gaussian_loglike, mh_sample,
+                    mh_sample_adapt, mlp_forward, philox4x32_10, uniform_logpdf)
+
+
+def test_k1_tf_float32_known_answer():
+    """K1: TF float32 predictions printed in surrogate_fft.ipynb cell 11 (10 rows x 15 outputs)."""
+    d = np.load(os.path.join(helpers.GOLDEN, "k1_fft.npz"))
+    pred = mlp_forward(helpers.layers_of(d), d["X_test_scaled"])
+    assert pred.shape == (10, 15) and pred.dtype == np.float32
+    # printed to ~7 significant digits on values of magnitude 1..1000
+    assert np.max(np.abs(pred - d["tf_pred"])) < 1e-3
+    assert np.max(np.abs(pred - d["tf_pred"]) / np.linalg.norm(d["tf_pred"], axis=1, keepdims=True)) < 2e-6
+
+
+def test_k2_real_params_pin():
+    """K2: X_test[10] printed as 'Real Params' in both identification notebooks."""
+    g, q = helpers.load_problem("geometric"), helpers.load_problem("qfactor")
+    assert np.allclose(g["x_true"], [0.345976, -0.423282, 30.139451], atol=5e-7)
+    assert np.allclose(q["x_true"], [0.239648, -0.115476, 30.857092, 0.571707], atol=5e-7)
+    assert len(g["time"]) == 150 and np.isclose(g["time"][1], 1e-5)
+
+
+def test_forward_closure_shapes_and_precision():
+    pb = helpers.load_problem("geometric")
+    f = helpers.oracle_forward(pb)
+    y = f(pb["x_true"])
+    assert y.shape == (150,) and y.dtype == np.float32
+    yb = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], pb["X_test"][:4])
+    for i in range(4):
+        assert np.allclose(yb[i], f(pb["X_test"][i]), rtol=0, atol=2e-5)
+    y64 = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], pb["x_true"][None], np.float64)[0]
+    assert np.max(np.abs(y64 - y)) < 5e-5
+    # the surrogate reproduces the held-out simulation it was trained to match
+    assert np.max(np.abs(y - pb["y_true"])) < 0.5
+
+
+def test_distributions_match_cuqi_semantics():
+    y = np.array([1.0, 2.0, 3.0])
+    f = np.array([1.5, 2.0, 2.0], np.float32)
+    want = -0.5 * (3 * np.log(0.5) + (0.25 + 0 + 1.0) / 0.5 + 3 * np.log(2 * np.pi))
+    assert np.isclose(gaussian_loglike(y, f, 0.5), want)
+    assert uniform_logpdf([0.5, 0.5], [0, 0], [1, 2]) == pytest.approx(np.log(0.5))
+    assert uniform_logpdf([1.0, 2.0], [0, 0], [1, 2]) == pytest.approx(np.log(0.5))   # bounds inclusive
+    assert uniform_logpdf([1.0000001, 0.5], [0, 0], [1, 2]) == -np.inf
+
+
+def test_decision_rule_edges():
+    assert decide(0.0, 1.0, 0.0)                 # log u = 0 accepted when ratio >= 0
+    assert decide(-0.5, -0.5, 0.0)               # ties accept (<=)
+    assert not decide(-0.4999, -0.5, 0.0)
+    assert not decide(-1e300, -np.inf, 0.0)      # outside the box: never accepted
+    assert decide(-1e300, np.inf, 0.0)
+    assert decide(-5.0, -np.inf, -np.inf)        # Python min(0, nan) == 0
+    assert decide(-745.0, 0.0, 0.0)              # u -> 0+
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32_10."""
+    f = lambda c, k: [int(v) for v in philox4x32_10(np.array(c, np.uint32), np.array(k, np.uint32))]
+    assert f([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert f([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert f([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_k3_k4_adaptive_mh_statistics():
+    """K3/K4: acceptance, adapted scale and posterior spread printed / saved by the geometric notebook."""
+    pb = helpers.load_problem("geometric")
+    logd = helpers.oracle_logd(pb)
+    L = np.linalg.cholesky(pb["cov"])
+    s, te, acc, sc = mh_sample_adapt(logd, pb["x_opts"][0], 6000, 0, rng=np.random.default_rng(0), chol=L)
+    assert s.shape == (3, 6000) and te.shape == (6000,)
+    assert 0.24 <= acc <= 0.30          # notebook: 0.269-0.280
+    assert 0.110 <= sc <= 0.145         # notebook: 0.1253-0.1315
+    g = helpers.pins()["geometric_sample_10"]
+    assert np.all(np.abs(s.std(axis=1) / np.array(g["std"]) - 1.0) < 0.25)
+    # the first window contains acc[0] = 1 and the scale only changes every Na = 600 updates
+    assert np.isfinite(te).all()
+
+
+def test_explicit_randomness_is_reproducible():
+    pb = helpers.load_problem("geometric")
+    logd = helpers.oracle_logd(pb)
+    rng = np.random.default_rng(5)
+    xi = rng.standard_normal((40, 3)) @ np.linalg.cholesky(pb["cov"]).T
+    lu = np.log(rng.random(40))
+    a = mh_sample(logd, pb["x_opts"][1], 41, 0, 0.12, xi=xi, log_u=lu, return_trace=True)
+    b = mh_sample(logd, pb["x_opts"][1], 41, 0, 0.12, xi=xi, log_u=lu, return_trace=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[4], b[4])
+    # states only ever move by scale*xi
+    moved = a[4][1:] == 1
+    d = np.diff(a[0], axis=1).T
+    assert np.allclose(d[moved], 0.12 * xi[moved]) and np.all(d[~moved] == 0)
+
+
+def test_cwmh_and_da_preserve_the_posterior():
+    """CWMH / DA are unpinned extensions: check them against plain MH on a cheap Gaussian target."""
+    mu, sd = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    logd = lambda x: float(-0.5 * np.sum(((x - mu) / sd) ** 2))
+    coarse = lambda x: float(-0.5 * np.sum(((x - mu * 0.9) / (sd * 1.3)) ** 2))
+    rng = np.random.default_rng(0)
+    N = 30000
+    s1 = mh_sample(logd, mu, N, 1000, 1.5, rng=rng, chol=np.diag(sd))[0]
+    s2 = cwmh_sample(logd, mu, N, 1000, scale=sd * 2.0, rng=rng)[0]
+    s3, _, acc, prom = da_sample(logd, coarse, mu, N, 1000, 1.5, rng=rng, chol=np.diag(sd))
+    for s in (s1, s2, s3):
+        assert np.all(np.abs(s.mean(axis=1) - mu) < 0.15 * sd)
+        assert np.all(np.abs(s.std(axis=1) / sd - 1.0) < 0.1)
+    assert 0 < acc <= prom <= 1
+
+
+@pytest.mark.skipif(not os.path.isdir(helpers.REF), reason="reference tree not mounted")
+def test_h5_reader_on_every_reference_model():
+    from mcmc_mems_b200 import h5lite
+    files = sorted(glob.glob(os.path.join(helpers.REF, "tests", "*", "models", "*.keras")))
+    assert len(files) == 9
+    for p in files:
+        L = h5lite.load_keras_dense_stack(p)
+        assert all(l.kernel.dtype == np.float32 for l in L)
+        assert [l.activation for l in L] == ["tanh"] * (len(L) - 1) + ["linear"]
+        for a, b in zip(L[:-1], L[1:]):
+            assert a.kernel.shape[1] == b.kernel.shape[0] == a.bias.shape[0]
+        name = os.path.basename(p)
+        if name == "model_sensitivity.keras":
+            assert [l.kernel.shape for l in L] == [(3, 32)] + [(32, 32)] * 3 + [(32, 1)]
+        elif name == "model_VoltageSignal.keras":
+            assert L[0].kernel.shape[0] in (4, 5) and L[-1].kernel.shape == (64, 1) and len(L) == 7
+        elif name.endswith("fft_angle.keras"):
+            assert L[-1].kernel.shape == (64, 8)
+        else:
+            assert L[-1].kernel.shape == (64, 15)
+    g = helpers.load_problem("geometric")
+    L = h5lite.load_keras_dense_stack(os.path.join(helpers.REF, "tests/Xaccelerometer_geometric/models/model_VoltageSignal.keras"))
+    for (k, b, a), l in zip(g["layers"], L):
+        assert np.array_equal(k, l.kernel) and np.array_equal(b, l.bias) and a == l.activation
+
+
+@pytest.mark.skipif(not os.path.isdir(helpers.REF), reason="reference tree not mounted")
+def test_preprocessing_mirror_reproduces_reference_constants(tmp_path):
+    from mcmc_mems_b200 import preprocessing
+    cwd = os.getcwd()
+    os.chdir(os.path.join(helpers.REF, "tests", "Xaccelerometer_geometric"))
+    try:
+        dp = preprocessing("./config_I.json")
+    finally:
+        os.chdir(cwd)
+    g = helpers.load_problem("geometric")
+    assert np.array_equal(dp.time, g["time"])
+    assert np.allclose(dp.scaler.mean_, g["scaler_mean"], rtol=1e-14)
+    assert np.allclose(dp.scaler.scale_, g["scaler_scale"], rtol=1e-14)
+    assert np.array_equal(dp.X_test[10], g["x_true"]) and np.array_equal(dp.y_test[10], g["y_true"])
+    assert dp.X_train_scaled.shape == (640 * 150, 4)
