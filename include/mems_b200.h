@@ -137,7 +137,8 @@ int  mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths,
 /* Hardware self-test of the tensor-core plumbing the MH kernels rely on (UMMA descriptors,
  * 128B swizzle, TMEM operand packing, tcgen05.ld/st, commit->mbarrier):
  * D[128][64] (f32) = A[128][64] (f16) * B[64][64]^T (f16), all device pointers, row-major.
- * variant 0: A operand written to TMEM by the threads (the product path), 1: A from shared memory. */
+ * variant 0: A operand written to TMEM by the threads (the product path), 1: A from shared memory,
+ * 2: the split chain A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with A = [A_hi; A_lo] (256x64), B = [W_hi; W_lo] (128x64). */
 int  mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev,
                         const void* b_f16_dev, float* d_out_dev, void* stream);
 

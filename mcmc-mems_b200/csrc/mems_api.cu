@@ -204,10 +204,11 @@ int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_m
 }
 
 int mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out, double* loglik_out, void* stream) {
-    if (!h || !x_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
     if (!h->have_weights || !h->have_problem) return fail(MEMS_E_STATE, "set weights and problem first");
     if (n < 0) return fail(MEMS_E_INVALID, "n < 0");
     if (n == 0) return MEMS_OK;
+    if (!x_dev) return fail(MEMS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, x_dev, n, y_out, loglik_out, 0)
@@ -362,7 +363,7 @@ int64_t mems_launch_count(mems_handle_t h) { return h ? h->launches : 0; }
 int mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev, const void* b_f16_dev, float* d_out_dev,
                        void* stream) {
     if (!a_f16_dev || !b_f16_dev || !d_out_dev) return fail(MEMS_E_INVALID, "null argument");
-    if (variant < 0 || variant > 1) return fail(MEMS_E_INVALID, "variant must be 0 (A in TMEM) or 1 (A in shared memory)");
+    if (variant < 0 || variant > 2) return fail(MEMS_E_INVALID, "variant must be 0 (A in TMEM), 1 (A in shared memory) or 2 (split chain)");
     CUDA_TRY(cudaSetDevice(device));
     const int e = mems_tc_selftest(variant, a_f16_dev, b_f16_dev, d_out_dev, reinterpret_cast<cudaStream_t>(stream));
     if (e != 0) return fail(MEMS_E_CUDA, "selftest launch failed: %s", cudaGetErrorString((cudaError_t)e));

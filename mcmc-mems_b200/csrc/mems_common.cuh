@@ -26,7 +26,7 @@ struct MemsProblem {
     int P, T;
     float W1[(MEMS_PMAX + 1) * MEMS_WIDTH];            // [P+1][64], Keras layout [in][out]
     float b1[MEMS_WIDTH];
-    float Wh[MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH]; // [l][k][n]
+    __align__(16) float Wh[MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH]; // [l][k][n]; float4 loads
     float bh[MEMS_NLAYER_H * MEMS_WIDTH];
     float w7[MEMS_WIDTH];
     float b7;
