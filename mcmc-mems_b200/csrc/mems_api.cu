@@ -54,6 +54,7 @@ namespace {
 
 int choose_nc(const MemsHandle_* h, int C) {
     if (h->cfg.chains_per_block > 0) return h->cfg.chains_per_block;
+    if (h->cfg.path == MEMS_PATH_TC) return mems_tc_choose_nc(C, h->host_pb.c.T, h->sm_count);
     int best = 1;
     long long best_cost = -1;
     for (int nc = 1; nc <= MEMS_NCMAX; nc <<= 1) {
@@ -117,8 +118,8 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
     memset(&h->host_pb, 0, sizeof(MemsProblem));
-    h->host_pb.P = cfg->n_params;
-    h->host_pb.T = cfg->n_time;
+    h->host_pb.c.P = cfg->n_params;
+    h->host_pb.c.T = cfg->n_time;
     const size_t C = (size_t)cfg->n_chains, P = (size_t)cfg->n_params;
     memset(&h->chains, 0, sizeof(MemsChains));
     h->chains.C = cfg->n_chains;
@@ -157,7 +158,7 @@ int mems_set_weights(mems_handle_t h, const float* const* W, const float* const*
         if (!W[l] || !b[l]) return fail(MEMS_E_INVALID, "null weight pointer for layer %d", l);
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     MemsProblem& pb = h->host_pb;
-    const int P = pb.P;
+    const int P = pb.c.P;
     memcpy(pb.W1, W[0], sizeof(float) * (P + 1) * MEMS_WIDTH);
     memcpy(pb.b1, b[0], sizeof(float) * MEMS_WIDTH);
     for (int l = 0; l < MEMS_NLAYER_H; ++l) {
@@ -180,20 +181,20 @@ int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_m
     if (!(sigma2 > 0.0)) return fail(MEMS_E_INVALID, "sigma2 must be positive");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     MemsProblem& pb = h->host_pb;
-    const int P = pb.P, T = pb.T;
+    const int P = pb.c.P, T = pb.c.T;
     for (int p = 0; p <= P; ++p) {
         if (!(scaler_scale[p] != 0.0)) return fail(MEMS_E_INVALID, "scaler_scale[%d] is zero", p);
-        pb.mean[p] = scaler_mean[p];
-        pb.sscale[p] = scaler_scale[p];
+        pb.c.mean[p] = scaler_mean[p];
+        pb.c.sscale[p] = scaler_scale[p];
     }
     for (int p = 0; p < P; ++p) {
         if (!(low[p] <= high[p])) return fail(MEMS_E_INVALID, "low[%d] > high[%d]", p, p);
-        pb.low[p] = low[p];
-        pb.high[p] = high[p];
+        pb.c.low[p] = low[p];
+        pb.c.high[p] = high[p];
     }
-    for (int i = 0; i < P * P; ++i) pb.chol[i] = chol[i];
-    pb.sigma2 = sigma2;
-    pb.neg_half_inv_sigma2 = -0.5 / sigma2;
+    for (int i = 0; i < P * P; ++i) pb.c.chol[i] = chol[i];
+    pb.c.sigma2 = sigma2;
+    pb.c.neg_half_inv_sigma2 = -0.5 / sigma2;
     std::vector<float> ts(T);
     // StandardScaler.transform on the time column in f64, then the Keras cast to f32 (utils.py:38-39)
     for (int t = 0; t < T; ++t) ts[t] = (float)((time[t] - scaler_mean[P]) / scaler_scale[P]);
@@ -242,7 +243,7 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
     h->steps_done = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int C = h->chains.C;
-    init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.P, x0_dev, scale0);
+    init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.c.P, x0_dev, scale0);
     CUDA_TRY(cudaGetLastError());
     MemsLaunchCtx ctx = make_ctx(h, stream);
     // target_eval[0] = logd(x0): likelihood + prior (-inf outside the box)
@@ -311,7 +312,7 @@ int mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale, ui
     if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.P;
+    const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.c.P;
     if (x) CUDA_TRY(cudaMemcpyAsync(x, h->chains.x, sizeof(double) * P * C, cudaMemcpyDeviceToDevice, st));
     if (loglik) CUDA_TRY(cudaMemcpyAsync(loglik, h->chains.ll, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
     if (scale) CUDA_TRY(cudaMemcpyAsync(scale, h->chains.scale, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));

@@ -22,18 +22,22 @@
 // ---------------------------------------------------------------------------------------
 // Read-only problem description, one copy per handle in global memory.
 // ---------------------------------------------------------------------------------------
-struct MemsProblem {
+struct MemsConsts {        // small scalar part: copied to shared memory by the kernels
     int P, T;
+    double mean[MEMS_PMAX + 1], sscale[MEMS_PMAX + 1]; // StandardScaler mean_/scale_
+    double low[MEMS_PMAX], high[MEMS_PMAX];
+    double chol[MEMS_PMAX * MEMS_PMAX];                // lower Cholesky factor of the proposal cov
+    double sigma2, neg_half_inv_sigma2;
+};
+
+struct MemsProblem {
+    MemsConsts c;
     float W1[(MEMS_PMAX + 1) * MEMS_WIDTH];            // [P+1][64], Keras layout [in][out]
     float b1[MEMS_WIDTH];
     __align__(16) float Wh[MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH]; // [l][k][n]; float4 loads
     float bh[MEMS_NLAYER_H * MEMS_WIDTH];
     float w7[MEMS_WIDTH];
     float b7;
-    double mean[MEMS_PMAX + 1], sscale[MEMS_PMAX + 1]; // StandardScaler mean_/scale_
-    double low[MEMS_PMAX], high[MEMS_PMAX];
-    double chol[MEMS_PMAX * MEMS_PMAX];                // lower Cholesky factor of the proposal cov
-    double sigma2, neg_half_inv_sigma2;
     const float* ts;                                   // [T] scaled time column, f32
     const double* yobs;                                // [T]
     const uint4* wimg;                                 // tensor-core path: pre-swizzled fp16 weight image
@@ -98,7 +102,7 @@ __device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, doubl
 // The randomness of update `step` of global chain `gid`: xi = chol*z (P values) and log u.
 // purpose 0: normals 0..3; purpose 1: word x = uniform of the accept test (words y,z,w reserved
 // for second-stage / per-component uniforms).
-__device__ __forceinline__ void draw_update(const MemsProblem& pb, unsigned long long seed,
+__device__ __forceinline__ void draw_update(const MemsConsts& pb, unsigned long long seed,
                                             unsigned long long gid, unsigned long long step,
                                             double* xi, double& log_u) {
     const unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
@@ -170,12 +174,12 @@ __device__ __forceinline__ void batch_store(const ChainBatch& cb, const MemsChai
 
 // Scale a parameter vector the way the reference does before the network call:
 // StandardScaler.transform in f64 (utils.py:38), then the Keras cast to f32 (utils.py:39).
-__device__ __forceinline__ float scale_param(const MemsProblem& pb, int p, double v) {
+__device__ __forceinline__ float scale_param(const MemsConsts& pb, int p, double v) {
     return (float)((v - pb.mean[p]) / pb.sscale[p]);
 }
 
 // Thread j proposes for chain c0+j at local update index s (global index step0+s).
-__device__ __forceinline__ void batch_propose(ChainBatch& cb, const MemsProblem& pb, const MemsChains& ch,
+__device__ __forceinline__ void batch_propose(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
                                               const MemsRunArgs& ra, int c0, int j, int s) {
     const int P = pb.P;
     const int c = c0 + j;
@@ -201,7 +205,7 @@ __device__ __forceinline__ void batch_propose(ChainBatch& cb, const MemsProblem&
 }
 
 // Thread j finishes update s of chain c0+j given S = sum_t (y_obs - f(x*))^2.
-__device__ __forceinline__ void batch_finish(ChainBatch& cb, const MemsProblem& pb, const MemsChains& ch,
+__device__ __forceinline__ void batch_finish(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
                                              const MemsRunArgs& ra, int c0, int j, int s, double S) {
     const int P = pb.P;
     const int c = c0 + j;
@@ -252,6 +256,7 @@ int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
 int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
                     int apply_prior);
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
+int mems_tc_choose_nc(int C, int T, int sm_count);
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);
 int mems_draw_launch(const MemsLaunchCtx& ctx, unsigned long long step0, int n_steps, double* xi_out,
                      double* log_u_out);

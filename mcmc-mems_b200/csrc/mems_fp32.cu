@@ -11,6 +11,7 @@ namespace {
 constexpr int NT = 256;   // threads per block
 
 struct Fp32Smem {
+    MemsConsts c;
     ChainBatch cb;
     float W1[(MEMS_PMAX + 1) * MEMS_WIDTH];
     float b1[MEMS_WIDTH];
@@ -24,13 +25,14 @@ struct Fp32Smem {
 
 __device__ __forceinline__ void load_constants(Fp32Smem& sm, const MemsProblem& pb, double* s_yobs, float* s_ts) {
     const int tid = threadIdx.x;
+    if (tid == 0) sm.c = pb.c;
     for (int i = tid; i < (MEMS_PMAX + 1) * MEMS_WIDTH; i += NT) sm.W1[i] = pb.W1[i];
     for (int i = tid; i < MEMS_WIDTH; i += NT) { sm.b1[i] = pb.b1[i]; sm.w7[i] = pb.w7[i]; }
     for (int i = tid; i < MEMS_NLAYER_H * MEMS_WIDTH; i += NT) sm.bh[i] = pb.bh[i];
     const float4* src = reinterpret_cast<const float4*>(pb.Wh);
     float4* dst = reinterpret_cast<float4*>(sm.Wh);
     for (int i = tid; i < MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH / 4; i += NT) dst[i] = src[i];
-    for (int i = tid; i < pb.T; i += NT) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+    for (int i = tid; i < pb.c.T; i += NT) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
 }
 
 // One surrogate row: scaled inputs (xs[0..P), ts) -> scalar output, everything in FP32.
@@ -107,9 +109,9 @@ fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs 
     Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(Fp32Smem));
-    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     load_constants(sm, pb, s_yobs, s_ts);
-    const int P = pb.P, T = pb.T, nc = ra.nc;
+    const int P = pb.c.P, T = pb.c.T, nc = ra.nc;
     const float b7 = pb.b7;
     const int tid = threadIdx.x;
     const int nbatch = (ch.C + nc - 1) / nc;
@@ -120,10 +122,10 @@ fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs 
         batch_load(sm.cb, ch, P, c0, tid, ncv);
         __syncthreads();
         for (int s = 0; s < ra.n_steps; ++s) {
-            if (tid < ncv) batch_propose(sm.cb, pb, ch, ra, c0, tid, s);
+            if (tid < ncv) batch_propose(sm.cb, sm.c, ch, ra, c0, tid, s);
             __syncthreads();
             eval_batch(sm, s_yobs, s_ts, P, T, b7, nc, ncv, true, nullptr, c0);
-            if (tid < ncv) batch_finish(sm.cb, pb, ch, ra, c0, tid, s, sm.Spart[tid]);
+            if (tid < ncv) batch_finish(sm.cb, sm.c, ch, ra, c0, tid, s, sm.Spart[tid]);
             __syncthreads();
         }
         batch_store(sm.cb, ch, P, c0, tid, ncv);
@@ -137,9 +139,9 @@ fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restric
     Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(Fp32Smem));
-    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     load_constants(sm, pb, s_yobs, s_ts);
-    const int P = pb.P, T = pb.T;
+    const int P = pb.c.P, T = pb.c.T;
     const int tid = threadIdx.x;
     const int nbatch = (n + nc - 1) / nc;
     for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
@@ -150,15 +152,15 @@ fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restric
             bool inb = true;
             for (int p = 0; p < P; ++p) {
                 const double v = x[(size_t)p * n + c0 + tid];
-                sm.cb.xs[p][tid] = scale_param(pb, p, v);
-                inb = inb && !(v < pb.low[p]) && !(v > pb.high[p]);
+                sm.cb.xs[p][tid] = scale_param(sm.c, p, v);
+                inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
             }
             sm.cb.inb[tid] = inb ? 1 : 0;
         }
         __syncthreads();
         eval_batch(sm, s_yobs, s_ts, P, T, pb.b7, nc, ncv, false, y_out, c0);
         if (tid < ncv && ll_out) {
-            const double ll = pb.neg_half_inv_sigma2 * sm.Spart[tid];
+            const double ll = sm.c.neg_half_inv_sigma2 * sm.Spart[tid];
             ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
         }
     }
@@ -166,7 +168,7 @@ fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restric
 
 __global__ void draw_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, unsigned long long step0,
                             int n_steps, double* xi_out, double* log_u_out) {
-    const MemsProblem& pb = *pbp;
+    const MemsConsts& pb = pbp->c;
     const size_t total = (size_t)n_steps * ch.C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(i / ch.C), c = (int)(i % ch.C);
@@ -218,7 +220,7 @@ size_t fp32_smem_bytes(int T) { return sizeof(Fp32Smem) + (size_t)T * (sizeof(do
 }  // namespace
 
 int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
-    const size_t smem = fp32_smem_bytes(ctx.pb_host->T);
+    const size_t smem = fp32_smem_bytes(ctx.pb_host->c.T);
     cudaError_t e = cudaFuncSetAttribute(fp32_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
@@ -229,7 +231,7 @@ int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
 
 int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
                       int apply_prior) {
-    const size_t smem = fp32_smem_bytes(ctx.pb_host->T);
+    const size_t smem = fp32_smem_bytes(ctx.pb_host->c.T);
     cudaError_t e = cudaFuncSetAttribute(fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     // spread the points over the SMs: smallest power-of-two batch that still fills the grid once

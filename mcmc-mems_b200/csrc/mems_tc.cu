@@ -27,9 +27,15 @@
 
 namespace {
 
-constexpr int NSLOT = 4;
-constexpr int NWORKER = NSLOT * 128;
-constexpr int NTHREADS = NWORKER + 32;
+// CTA organisation: two independent worker groups; each owns one batch of chains at a time, two TMEM
+// tile slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and its own MMA
+// issuer warp.  Groups never synchronise with each other, so one group's accept/reject section
+// overlaps the other group's tensor work.
+constexpr int NGROUP = 2;
+constexpr int GSLOT = 2;                       // tile slots per group
+constexpr int GTHREADS = 128;                  // 4 worker warps per group = the 4 TMEM lane quarters
+constexpr int NWORKER = NGROUP * GTHREADS;     // 256
+constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -45,18 +51,23 @@ constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
 // instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+struct GroupSmem {
+    ChainBatch cb;
+    double Spart[GTHREADS];
+    unsigned long long bar_A[GSLOT];   // workers -> MMA issuer: A operand of the slot is in TMEM
+    unsigned long long bar_D[GSLOT];   // tensor core -> workers: accumulator of the slot is complete
+};
+
 struct TcSmem {
     __align__(1024) unsigned char wimg[NBLK * BLK];
     float w7[64];
     float b7;
     float pad_[3];
-    ChainBatch cb;
-    double Spart[NWORKER];
-    unsigned long long bar_A[NSLOT];
-    unsigned long long bar_D[NSLOT];
+    MemsConsts c;
+    GroupSmem grp[NGROUP];
     unsigned long long bar_w;
     uint32_t tmem_base;
-    uint32_t err_flag;
+    uint32_t pad2_;
     // followed by: double yobs[T]; float ts[T];
 };
 
@@ -144,7 +155,7 @@ __device__ __forceinline__ void umma_commit(void* bar) {
                  ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -195,7 +206,7 @@ __device__ __forceinline__ void tanh4(const uint32_t* v, float* t) {
 }
 
 // 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
-__device__ __forceinline__ void epilogue_split(const uint32_t (&v)[32], uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+__device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
         float t[4];
@@ -214,7 +225,7 @@ __device__ __forceinline__ void epilogue_split(const uint32_t (&v)[32], uint32_t
 }
 
 // 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights
-__device__ __forceinline__ float epilogue_dot(const uint32_t (&v)[32], const float* w7c, float acc) {
+__device__ __forceinline__ float epilogue_dot(const uint32_t* v, const float* w7c, float acc) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
         float t[4];
@@ -263,35 +274,24 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// Serve `units[s]` (tile, layer) requests of every slot, in whatever order their operands arrive.
-__device__ void mma_service(TcSmem& sm, const long long (&units)[NSLOT]) {
+// MMA issuer of one group: serves the group's two slots in the fixed order the workers produce them.
+__device__ __forceinline__ void mma_serve_eval(TcSmem& sm, GroupSmem& gs, int g, int n_tiles, uint32_t& phA) {
     const uint32_t wimg = smem_u32(sm.wimg);
-    const uint32_t base = sm.tmem_base;
-    long long cnt[NSLOT];
-    uint32_t ph[NSLOT];
-    long long remaining = 0;
+    const uint32_t base = sm.tmem_base + (uint32_t)(g * GSLOT * 128);
+    const int n_pairs = (n_tiles + 1) >> 1;
+    for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+        for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
-    for (int s = 0; s < NSLOT; ++s) { cnt[s] = 0; ph[s] = 0; remaining += units[s]; }
-    long long idle_t0 = clock64();
-    while (remaining > 0) {
-        bool any = false;
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-            if (cnt[s] < units[s] && mbar_test(&sm.bar_A[s], ph[s])) {
-                tc_fence_after();
-                issue_layer(wimg, base + s * 128, (int)(cnt[s] % MEMS_HIDDEN));
-                umma_commit(&sm.bar_D[s]);
-                ph[s] ^= 1u;
-                cnt[s] += 1;
-                remaining -= 1;
-                any = true;
+            for (int s = 0; s < GSLOT; ++s) {
+                if (pair * 2 + s < n_tiles) {
+                    mbar_wait(&gs.bar_A[s], (phA >> s) & 1u);
+                    phA ^= (1u << s);
+                    tc_fence_after();
+                    issue_layer(wimg, base + s * 128, layer);
+                    umma_commit(&gs.bar_D[s]);
+                }
             }
-        }
-        if (any) {
-            idle_t0 = clock64();
-        } else {
-            __nanosleep(20);
-            if (clock64() - idle_t0 > 4000000000LL) __trap();
         }
     }
 }
@@ -299,11 +299,6 @@ __device__ void mma_service(TcSmem& sm, const long long (&units)[NSLOT]) {
 // ------------------------------------------------------------------------------------------
 // Worker side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
 // ------------------------------------------------------------------------------------------
-template <int P>
-struct RowInputs {          // the layer-1 A operand of one row, K=32 fp16 = 16 packed words
-    uint32_t a1[16];
-};
-
 // K-slot of (term, input) in the layer-1 operand: terms 0..2 multiply W_hi, 3..4 multiply W_lo
 template <int P>
 __device__ __forceinline__ constexpr int k1_slot(int term, int i) { return term * (P + 1) + i; }
@@ -327,91 +322,108 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
     set_half<P>(a1, k1_slot<P>(4, i), m);
 }
 
+__device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
+
+// The 128 threads of group g evaluate one batch.  Thread gt owns TMEM lane gt of both slots;
+// row gt of every tile is (chain j = gt mod nc, time sub-row gt / nc).
 template <int P>
-__device__ __forceinline__ void tc_eval_batch(TcSmem& sm, const double* s_yobs, const float* s_ts, int T, int nc,
-                                              int log2nc, int ncv, bool skip_dead, float* y_out, int c0,
-                                              uint32_t& phaseD) {
-    const int wtid = threadIdx.x;
-    const int warp = wtid >> 5, lane = wtid & 31;
-    const int slot = warp >> 2, q = warp & 3;
-    const int row = q * 32 + lane;
-    const int j = row & (nc - 1);
-    const int sub = row >> log2nc;
+__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
+                                              const float* s_ts, int T, int nc, int log2nc, int ncv, bool skip_dead,
+                                              float* y_out, int c0, uint32_t& phD) {
+    const int gt = threadIdx.x & (GTHREADS - 1);
+    const int q = gt >> 5;
+    const int j = gt & (nc - 1);
+    const int sub = gt >> log2nc;
     const int tpt = 128 >> log2nc;                    // time points per tile
     const int n_tiles = (T + tpt - 1) / tpt;
-    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
-    const bool chain_live = (j < ncv) && (!skip_dead || sm.cb.inb[j]);
+    const int n_pairs = (n_tiles + 1) >> 1;
+    const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
+    const bool chain_live = (j < ncv) && (!skip_dead || gs.cb.inb[j]);
 
     uint32_t a1[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) a1[i] = 0u;
 #pragma unroll
-    for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? sm.cb.xs[p][j] : 0.0f);
+    for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? gs.cb.xs[p][j] : 0.0f);
     set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);           // ones that pick up b_hi, b_mid, b_lo
     set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
     set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
 
-    double Sp = 0.0;
-    for (int tile = slot; tile < n_tiles; tile += NSLOT) {
-        const int t = tile * tpt + sub;
-        const bool live = chain_live && (t < T);
-        put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
-        tmem_st16(tD + 64, a1);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&sm.bar_A[slot]);
+    // prologue: layer-1 operands of the first tile of each slot
+#pragma unroll
+    for (int s = 0; s < GSLOT; ++s) {
+        if (s < n_tiles) {
+            const int t = s * tpt + sub;
+            put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
+            tmem_st16(tD0 + s * 128 + 64, a1);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&gs.bar_A[s]);
+        }
+    }
 
-        float out = 0.0f;
+    double Sp = 0.0;
+    float out[GSLOT] = {0.0f, 0.0f};
+    for (int pair = 0; pair < n_pairs; ++pair) {
 #pragma unroll 1
         for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
-            mbar_wait(&sm.bar_D[slot], phaseD);
-            phaseD ^= 1u;
-            tc_fence_after();
-            if (layer < MEMS_HIDDEN - 1) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32], hi2[16], lo2[16];
-                    tmem_ld32(tD + 32 * c, v);
+            for (int s = 0; s < GSLOT; ++s) {
+                const int tile = pair * 2 + s;
+                if (tile < n_tiles) {
+                    const uint32_t tD = tD0 + s * 128;
+                    mbar_wait(&gs.bar_D[s], (phD >> s) & 1u);
+                    phD ^= (1u << s);
+                    tc_fence_after();
+                    uint32_t v[64];
+                    tmem_ld32(tD, v);
+                    tmem_ld32(tD + 32, v + 32);
                     tc_wait_ld();
-                    epilogue_split(v, hi2, lo2);
-                    tmem_st16(tD + 64 + 16 * c, hi2);
-                    tmem_st16(tD + 96 + 16 * c, lo2);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(&sm.bar_A[slot]);
-            } else {
+                    if (layer < MEMS_HIDDEN - 1) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(tD + 32 * c, v);
-                    tc_wait_ld();
-                    out = epilogue_dot(v, sm.w7 + 32 * c, out);
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t hi2[16], lo2[16];
+                            epilogue_split(v + 32 * c, hi2, lo2);
+                            tmem_st16(tD + 64 + 16 * c, hi2);
+                            tmem_st16(tD + 96 + 16 * c, lo2);
+                        }
+                        tc_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(&gs.bar_A[s]);
+                    } else {
+                        float o = epilogue_dot(v, sm.w7, 0.0f);
+                        o = epilogue_dot(v + 32, sm.w7 + 32, o) + sm.b7;
+                        const int t = tile * tpt + sub;
+                        if (chain_live && t < T) {
+                            if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                            const double r = s_yobs[t] - (double)o;
+                            Sp = fma(r, r, Sp);
+                        }
+                        // this slot's D and A are free again: stage the layer-1 operand of its next tile
+                        const int nt = tile + GSLOT;
+                        if (nt < n_tiles) {
+                            const int t2 = nt * tpt + sub;
+                            put_input<P>(a1, P, s_ts[t2 < T ? t2 : T - 1]);
+                            tmem_st16(tD + 64, a1);
+                            tc_wait_st();
+                            tc_fence_before();
+                            mbar_arrive(&gs.bar_A[s]);
+                        } else {
+                            tc_fence_before();
+                        }
+                    }
                 }
-                // the slot's D and A regions are free again: every read of this tile has completed
-                tc_fence_before();
             }
         }
-        out += sm.b7;
-        if (live) {
-            if (y_out) y_out[(size_t)(c0 + j) * T + t] = out;
-            const double r = s_yobs[t] - (double)out;
-            Sp = fma(r, r, Sp);
-        }
     }
-    sm.Spart[wtid] = Sp;
-    named_bar_sync(1, NWORKER);
-    if (wtid < nc) {
-        // fixed summation order: slot-major, then time sub-row
-        double S = 0.0;
-        for (int s = 0; s < NSLOT; ++s)
-            for (int u = 0; u < tpt; ++u) S += sm.Spart[s * 128 + u * nc + wtid];
-        sm.Spart[wtid] = S;   // thread wtid only ever reads slots {s*128 + u*nc + wtid}: no cross-thread hazard
+    (void)out;
+    gs.Spart[gt] = Sp;
+    group_bar_sync(g);
+    if (gt < nc) {
+        double S = 0.0;                                // fixed order: time sub-rows ascending
+        for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nc + gt];
+        gs.Spart[gt] = S;   // thread gt only ever reads slots {u*nc + gt}: no cross-thread hazard
     }
-}
-
-__device__ __forceinline__ long long tiles_of_slot(int n_tiles, int s) {
-    return (n_tiles > s) ? (long long)((n_tiles - s + NSLOT - 1) / NSLOT) : 0;
 }
 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
@@ -421,9 +433,10 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < NSLOT; ++s) { mbar_init(&sm.bar_A[s], 128); mbar_init(&sm.bar_D[s], 1); }
+        for (int g = 0; g < NGROUP; ++g)
+            for (int s = 0; s < GSLOT; ++s) { mbar_init(&sm.grp[g].bar_A[s], GTHREADS); mbar_init(&sm.grp[g].bar_D[s], 1); }
         mbar_init(&sm.bar_w, 1);
-        sm.err_flag = 0;
+        sm.c = pb.c;
         fence_barrier_init();
     }
     __syncthreads();
@@ -438,7 +451,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
             bulk_g2s(sm.w7, src + (size_t)NBLK * BLK, WIMG_TAIL, &sm.bar_w);
         }
     }
-    for (int i = tid; i < pb.T; i += NTHREADS) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+    for (int i = tid; i < pb.c.T; i += NTHREADS) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -461,39 +474,40 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
-    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     tc_prologue(sm, pb, s_yobs, s_ts);
 
-    const int T = pb.T, nc = ra.nc, log2nc = ilog2(ra.nc);
+    const int T = sm.c.T, nc = ra.nc, log2nc = ilog2(ra.nc);
     const int tid = threadIdx.x;
     const int nbatch = (ch.C + nc - 1) / nc;
-    const int my_batches = (nbatch > (int)blockIdx.x) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int tpt = 128 >> log2nc;
     const int n_tiles = (T + tpt - 1) / tpt;
+    const int g = (tid < NWORKER) ? (tid >> 7) : ((tid - NWORKER) >> 5);
+    GroupSmem& gs = sm.grp[g];
+    const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NWORKER) {
         if ((tid & 31) == 0) {
-            long long units[NSLOT];
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s)
-                units[s] = (long long)my_batches * ra.n_steps * tiles_of_slot(n_tiles, s) * MEMS_HIDDEN;
-            mma_service(sm, units);
+            uint32_t phA = 0;
+            for (int batch = gid; batch < nbatch; batch += gstride)
+                for (int s = 0; s < ra.n_steps; ++s) mma_serve_eval(sm, gs, g, n_tiles, phA);
         }
         __syncwarp();
     } else {
-        uint32_t phaseD = 0;
-        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int gt = tid & (GTHREADS - 1);
+        uint32_t phD = 0;
+        for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, ch.C - c0);
-            named_bar_sync(1, NWORKER);
-            batch_load(sm.cb, ch, P, c0, tid, ncv);
+            group_bar_sync(g);
+            batch_load(gs.cb, ch, P, c0, gt, ncv);
             for (int s = 0; s < ra.n_steps; ++s) {
-                if (tid < ncv) batch_propose(sm.cb, pb, ch, ra, c0, tid, s);
-                named_bar_sync(1, NWORKER);
-                tc_eval_batch<P>(sm, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phaseD);
-                if (tid < ncv) batch_finish(sm.cb, pb, ch, ra, c0, tid, s, sm.Spart[tid]);
+                if (gt < ncv) batch_propose(gs.cb, sm.c, ch, ra, c0, gt, s);
+                group_bar_sync(g);
+                tc_eval_group<P>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phD);
+                if (gt < ncv) batch_finish(gs.cb, sm.c, ch, ra, c0, gt, s, gs.Spart[gt]);
             }
-            batch_store(sm.cb, ch, P, c0, tid, ncv);
+            batch_store(gs.cb, ch, P, c0, gt, ncv);
         }
     }
     tc_epilogue_free(sm);
@@ -507,44 +521,45 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
-    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.T);
+    float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     tc_prologue(sm, pb, s_yobs, s_ts);
 
-    const int T = pb.T, log2nc = ilog2(nc);
+    const int T = sm.c.T, log2nc = ilog2(nc);
     const int tid = threadIdx.x;
     const int nbatch = (n + nc - 1) / nc;
-    const int my_batches = (nbatch > (int)blockIdx.x) ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int tpt = 128 >> log2nc;
     const int n_tiles = (T + tpt - 1) / tpt;
+    const int g = (tid < NWORKER) ? (tid >> 7) : ((tid - NWORKER) >> 5);
+    GroupSmem& gs = sm.grp[g];
+    const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NWORKER) {
         if ((tid & 31) == 0) {
-            long long units[NSLOT];
-#pragma unroll
-            for (int s = 0; s < NSLOT; ++s) units[s] = (long long)my_batches * tiles_of_slot(n_tiles, s) * MEMS_HIDDEN;
-            mma_service(sm, units);
+            uint32_t phA = 0;
+            for (int batch = gid; batch < nbatch; batch += gstride) mma_serve_eval(sm, gs, g, n_tiles, phA);
         }
         __syncwarp();
     } else {
-        uint32_t phaseD = 0;
-        for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int gt = tid & (GTHREADS - 1);
+        uint32_t phD = 0;
+        for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, n - c0);
-            named_bar_sync(1, NWORKER);
-            if (tid < ncv) {
+            group_bar_sync(g);
+            if (gt < ncv) {
                 bool inb = true;
                 for (int p = 0; p < P; ++p) {
-                    const double v = x[(size_t)p * n + c0 + tid];
-                    sm.cb.xs[p][tid] = scale_param(pb, p, v);
-                    inb = inb && !(v < pb.low[p]) && !(v > pb.high[p]);
+                    const double v = x[(size_t)p * n + c0 + gt];
+                    gs.cb.xs[p][gt] = scale_param(sm.c, p, v);
+                    inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
                 }
-                sm.cb.inb[tid] = inb ? 1 : 0;
+                gs.cb.inb[gt] = inb ? 1 : 0;
             }
-            named_bar_sync(1, NWORKER);
-            tc_eval_batch<P>(sm, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phaseD);
-            if (tid < ncv && ll_out) {
-                const double ll = pb.neg_half_inv_sigma2 * sm.Spart[tid];
-                ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
+            group_bar_sync(g);
+            tc_eval_group<P>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phD);
+            if (gt < ncv && ll_out) {
+                const double ll = sm.c.neg_half_inv_sigma2 * gs.Spart[gt];
+                ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
             }
         }
     }
@@ -696,11 +711,26 @@ inline void put(unsigned char* img, int blk, int row, int k, double v) {
 
 size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
 
+// Chains per group batch (power of two): minimise (waves of batches over the 2*SMs groups) x (tile pairs per step).
+int mems_tc_choose_nc(int C, int T, int sm_count) {
+    int best = 1;
+    long long best_cost = -1;
+    for (int nc = 1; nc <= MEMS_NCMAX; nc <<= 1) {
+        const long long nbatch = (C + nc - 1) / nc;
+        const long long waves = (nbatch + (long long)NGROUP * sm_count - 1) / ((long long)NGROUP * sm_count);
+        const int tpt = 128 / nc;
+        const long long tiles = (T + tpt - 1) / tpt;
+        const long long cost = waves * ((tiles + 1) / 2) * 2;
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nc; }
+    }
+    return best;
+}
+
 // Build the shared-memory image: 128B-swizzled fp16 operand blocks + the FP32 output layer.
 void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
     unsigned char* img = static_cast<unsigned char*>(host_img);
     memset(img, 0, WIMG_BYTES);
-    const int P = pb.P, nin = P + 1;
+    const int P = pb.c.P, nin = P + 1;
     // layer 1: rows n (output neuron), K slots as in k1_slot(): terms 0..2 carry W_hi, 3..4 W_lo
     for (int n = 0; n < MEMS_WIDTH; ++n) {
         for (int i = 0; i < nin; ++i) {
@@ -743,20 +773,21 @@ void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
 }
 
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
-    const size_t smem = tc_smem_bytes(ctx.pb_host->T);
+    const size_t smem = tc_smem_bytes(ctx.pb_host->c.T);
     const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
-    const int grid = nbatch < ctx.sm_count ? nbatch : ctx.sm_count;
-    MEMS_LAUNCH_P(tc_run_kernel, ctx.pb_host->P, grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
+    const int want = (nbatch + NGROUP - 1) / NGROUP;
+    const int grid = want < ctx.sm_count ? want : ctx.sm_count;
+    MEMS_LAUNCH_P(tc_run_kernel, ctx.pb_host->c.P, grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
 }
 
 int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
                     int apply_prior) {
-    const size_t smem = tc_smem_bytes(ctx.pb_host->T);
-    int nc = MEMS_NCMAX;
-    while (nc > 1 && (n + nc - 1) / nc < ctx.sm_count) nc >>= 1;
+    const size_t smem = tc_smem_bytes(ctx.pb_host->c.T);
+    const int nc = mems_tc_choose_nc(n, ctx.pb_host->c.T, ctx.sm_count);
     const int nbatch = (n + nc - 1) / nc;
-    const int grid = nbatch < ctx.sm_count ? nbatch : ctx.sm_count;
-    MEMS_LAUNCH_P(tc_forward_kernel, ctx.pb_host->P, (grid > 0 ? grid : 1), smem, ctx.stream, ctx.pb_dev, x_dev, n, nc,
+    const int want = (nbatch + NGROUP - 1) / NGROUP;
+    const int grid = want < ctx.sm_count ? want : ctx.sm_count;
+    MEMS_LAUNCH_P(tc_forward_kernel, ctx.pb_host->c.P, (grid > 0 ? grid : 1), smem, ctx.stream, ctx.pb_dev, x_dev, n, nc,
                   y_out, ll_out, apply_prior);
 }
 
