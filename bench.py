@@ -172,7 +172,7 @@ def workload_config(args, P, cores_note=None):
            "3-param posterior, 4096 parallel chains on 1 B200" if args.workload == "geometric_4096" else args.workload,
            "n_params": P, "time_points": args.time_points, "chains_per_gpu": args.chains,
            "mh_updates_per_step": args.inner, "thin": args.thin, "sigma2": 0.005 if P == 3 else 0.5,
-           "proposal_scale": 0.128, "adaptation": "frozen", "surrogate": f"[{P + 1}]->64x6 tanh->1 (reference weights)",
+           "proposal_scale": 0.128, "adaptation": "frozen", "x0": "LSQ optima + one proposal step of jitter", "surrogate": f"[{P + 1}]->64x6 tanh->1 (reference weights)",
            "l2": "flushed between timed steps (256 MiB write, untimed); working set is on-chip"}
     if cores_note:
         cfg["cpu"] = cores_note
@@ -208,8 +208,12 @@ def run_ours(args):
     n_keep = S // thin
     path = PATH_TC if args.path == "tc" else PATH_FP32
     eng = helpers.engine(pb, C, path, device=local)
+    # chains start like the notebook's (identification.ipynb cell 12-14): at the least-squares optima,
+    # here jittered by one proposal step so that the C chains are distinct
     rng = np.random.default_rng(1)
-    x0_all = rng.uniform(pb["low"], pb["high"], size=(C * world, P))
+    Lc = np.linalg.cholesky(pb["cov"])
+    x0_all = pb["x_opts"][np.arange(C * world) % len(pb["x_opts"])] + 0.128 * rng.standard_normal((C * world, P)) @ Lc.T
+    x0_all = np.clip(x0_all, pb["low"], pb["high"])
     c0, c1 = D.shard_range(C * world, rank, world)
     x0_host = torch.from_numpy(np.ascontiguousarray(x0_all[c0:c1].T)).pin_memory()      # [P][C]
     seed = 0x5EED0000

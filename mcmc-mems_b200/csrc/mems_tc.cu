@@ -98,9 +98,9 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
     return ok != 0;
 }
 // Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
@@ -189,52 +189,68 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2): two lanes of work per issue slot
+__device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 // tanh of four accumulator values that already hold 2*log2(e)*z:  t = 1 - 2/(2^y + 1).
-// One MUFU.RCP is shared by the four (products stay < 2^104 thanks to the clamp).
-__device__ __forceinline__ void tanh4(const uint32_t* v, float* t) {
-    float d0 = ex2_approx(fminf(__uint_as_float(v[0]), EXP2_CLAMP)) + 1.0f;
-    float d1 = ex2_approx(fminf(__uint_as_float(v[1]), EXP2_CLAMP)) + 1.0f;
-    float d2 = ex2_approx(fminf(__uint_as_float(v[2]), EXP2_CLAMP)) + 1.0f;
-    float d3 = ex2_approx(fminf(__uint_as_float(v[3]), EXP2_CLAMP)) + 1.0f;
-    const float p01 = d0 * d1, p23 = d2 * d3;
+// One MUFU.RCP is shared by the four (products stay < 2^104 thanks to the clamp).  Results come back
+// as the pairs TX = (t0, t2), TY = (t1, t3).
+__device__ __forceinline__ void tanh4(const uint32_t* v, uint64_t& TX, uint64_t& TY) {
+    const float e0 = ex2_approx(fminf(__uint_as_float(v[0]), EXP2_CLAMP));
+    const float e1 = ex2_approx(fminf(__uint_as_float(v[1]), EXP2_CLAMP));
+    const float e2 = ex2_approx(fminf(__uint_as_float(v[2]), EXP2_CLAMP));
+    const float e3 = ex2_approx(fminf(__uint_as_float(v[3]), EXP2_CLAMP));
+    const uint64_t one2 = pk(1.0f, 1.0f);
+    const uint64_t X = add2(pk(e0, e2), one2);          // (d0, d2)
+    const uint64_t Y = add2(pk(e1, e3), one2);          // (d1, d3)
+    float p01, p23;
+    upk(mul2(X, Y), p01, p23);
     const float r = rcp_approx(p01 * p23);
-    const float r01 = r * p23, r23 = r * p01;
-    t[0] = fmaf(r01 * d1, -2.0f, 1.0f);
-    t[1] = fmaf(r01 * d0, -2.0f, 1.0f);
-    t[2] = fmaf(r23 * d3, -2.0f, 1.0f);
-    t[3] = fmaf(r23 * d2, -2.0f, 1.0f);
+    const uint64_t R = pk(r * p23, r * p01);            // (1/(d0 d1), 1/(d2 d3))
+    const uint64_t m2 = pk(-2.0f, -2.0f);
+    TX = fma2(mul2(R, Y), m2, one2);                    // (t0, t2)
+    TY = fma2(mul2(R, X), m2, one2);                    // (t1, t3)
 }
 
 // 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
 __device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        float t[4];
-        tanh4(&v[4 * g], t);
-        float h[4], l[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);   // top 11 significant bits: exact in fp16
-            l[i] = t[i] - h[i];
-        }
-        hi2[2 * g] = pack_half2(h[0], h[1]);
-        hi2[2 * g + 1] = pack_half2(h[2], h[3]);
-        lo2[2 * g] = pack_half2(l[0], l[1]);
-        lo2[2 * g + 1] = pack_half2(l[2], l[3]);
+        uint64_t TX, TY;
+        tanh4(&v[4 * g], TX, TY);
+        float t0, t1, t2, t3;
+        upk(TX, t0, t2);
+        upk(TY, t1, t3);
+        // top 11 significant bits: exactly representable in fp16; the remainder goes to the lo operand
+        const float h0 = __uint_as_float(__float_as_uint(t0) & 0xFFFFE000u);
+        const float h1 = __uint_as_float(__float_as_uint(t1) & 0xFFFFE000u);
+        const float h2 = __uint_as_float(__float_as_uint(t2) & 0xFFFFE000u);
+        const float h3 = __uint_as_float(__float_as_uint(t3) & 0xFFFFE000u);
+        float l0, l1, l2, l3;
+        upk(sub2(TX, pk(h0, h2)), l0, l2);
+        upk(sub2(TY, pk(h1, h3)), l1, l3);
+        hi2[2 * g] = pack_half2(h0, h1);
+        hi2[2 * g + 1] = pack_half2(h2, h3);
+        lo2[2 * g] = pack_half2(l0, l1);
+        lo2[2 * g + 1] = pack_half2(l2, l3);
     }
 }
 
-// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights
-__device__ __forceinline__ float epilogue_dot(const uint32_t* v, const float* w7c, float acc) {
+// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights.
+// w7p holds the weights permuted per group of four as (w0, w2, w1, w3) to match the (TX, TY) pairing.
+__device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float* w7p, uint64_t acc) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-        float t[4];
-        tanh4(&v[4 * g], t);
-        const float4 w = *reinterpret_cast<const float4*>(w7c + 4 * g);
-        acc = fmaf(t[0], w.x, acc);
-        acc = fmaf(t[1], w.y, acc);
-        acc = fmaf(t[2], w.z, acc);
-        acc = fmaf(t[3], w.w, acc);
+        uint64_t TX, TY;
+        tanh4(&v[4 * g], TX, TY);
+        const float4 w = *reinterpret_cast<const float4*>(w7p + 4 * g);
+        acc = fma2(TX, pk(w.x, w.y), acc);
+        acc = fma2(TY, pk(w.z, w.w), acc);
     }
     return acc;
 }
@@ -363,7 +379,6 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     }
 
     double Sp = 0.0;
-    float out[GSLOT] = {0.0f, 0.0f};
     for (int pair = 0; pair < n_pairs; ++pair) {
 #pragma unroll 1
         for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
@@ -391,8 +406,9 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         tc_fence_before();
                         mbar_arrive(&gs.bar_A[s]);
                     } else {
-                        float o = epilogue_dot(v, sm.w7, 0.0f);
-                        o = epilogue_dot(v + 32, sm.w7 + 32, o) + sm.b7;
+                        float oa, ob;
+                        upk(epilogue_dot(v + 32, sm.w7 + 32, epilogue_dot(v, sm.w7, pk(0.0f, 0.0f))), oa, ob);
+                        const float o = (oa + ob) + sm.b7;
                         const int t = tile * tpt + sub;
                         if (chain_live && t < T) {
                             if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
@@ -416,7 +432,6 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             }
         }
     }
-    (void)out;
     gs.Spart[gt] = Sp;
     group_bar_sync(g);
     if (gt < nc) {
@@ -768,7 +783,11 @@ void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
     for (int m = 0; m < 128; ++m)
         for (int k = 0; k < 3; ++k) put(img, BLK_ONES + (m >> 6), m & 63, k, 1.0);
     float* tail = reinterpret_cast<float*>(img + (size_t)NBLK * BLK);
-    for (int k = 0; k < MEMS_WIDTH; ++k) tail[k] = pb.w7[k];
+    for (int k = 0; k < MEMS_WIDTH; ++k) {          // per group of four: (w0, w2, w1, w3), see epilogue_dot
+        const int g4 = k & ~3, i = k & 3;
+        const int perm = (i == 1) ? 2 : (i == 2) ? 1 : i;
+        tail[g4 + perm] = pb.w7[k];
+    }
     tail[MEMS_WIDTH] = pb.b7;
 }
 
