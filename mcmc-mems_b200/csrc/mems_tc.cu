@@ -21,6 +21,7 @@
 // Reference semantics: see mems_common.cuh header (src/InverseProblems/utils.py:30-40 etc.).
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "mems_common.cuh"
@@ -33,9 +34,11 @@ namespace {
 // overlaps the other group's tensor work.
 constexpr int NGROUP = 2;
 constexpr int GSLOT = 2;                       // tile slots per group
-constexpr int GTHREADS = 128;                  // 4 worker warps per group = the 4 TMEM lane quarters
-constexpr int NWORKER = NGROUP * GTHREADS;     // 256
-constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group
+// NH = worker warps per TMEM lane quarter: 1 -> a thread owns a whole 64-column row of the tile,
+// 2 -> two threads split the row (32 columns each), doubling the warps the scheduler can interleave.
+__host__ __device__ constexpr int gthreads(int NH) { return 128 * NH; }                 // worker threads per group
+__host__ __device__ constexpr int nworker(int NH) { return NGROUP * gthreads(NH); }
+__host__ __device__ constexpr int nthreads(int NH) { return nworker(NH) + 32 * NGROUP; } // + one MMA issuer warp per group
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -53,9 +56,11 @@ constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct GroupSmem {
     ChainBatch cb;
-    double Spart[GTHREADS];
+    double Spart[128];
+    float xchg[GSLOT][128];            // NH=2: partial output-layer dot of the upper column half
     unsigned long long bar_A[GSLOT];   // workers -> MMA issuer: A operand of the slot is in TMEM
     unsigned long long bar_D[GSLOT];   // tensor core -> workers: accumulator of the slot is complete
+    unsigned long long bar_X[GSLOT][4]; // NH=2: upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
 };
 
 struct TcSmem {
@@ -338,18 +343,22 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
     set_half<P>(a1, k1_slot<P>(4, i), m);
 }
 
-__device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
+template <int NH>
+__device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, gthreads(NH)); }
 
-// The 128 threads of group g evaluate one batch.  Thread gt owns TMEM lane gt of both slots;
-// row gt of every tile is (chain j = gt mod nc, time sub-row gt / nc).
-template <int P>
+// The worker threads of group g evaluate one batch.  Thread (row, h) owns TMEM lane `row` of both slots and
+// columns [64/NH * h, 64/NH * (h+1)) of it; row `row` of every tile is (chain j = row mod nc, time sub-row row / nc).
+template <int P, int NH>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
                                               const float* s_ts, int T, int nc, int log2nc, int ncv, bool skip_dead,
                                               float* y_out, int c0, uint32_t& phD) {
-    const int gt = threadIdx.x & (GTHREADS - 1);
-    const int q = gt >> 5;
-    const int j = gt & (nc - 1);
-    const int sub = gt >> log2nc;
+    constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
+    const int gt = threadIdx.x & (gthreads(NH) - 1);
+    const int row = gt & 127;
+    const int h = gt >> 7;                            // column half (always 0 when NH == 1)
+    const int q = row >> 5;
+    const int j = row & (nc - 1);
+    const int sub = row >> log2nc;
     const int tpt = 128 >> log2nc;                    // time points per tile
     const int n_tiles = (T + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
@@ -357,22 +366,26 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const bool chain_live = (j < ncv) && (!skip_dead || gs.cb.inb[j]);
 
     uint32_t a1[16];
+    if (h == 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a1[i] = 0u;
+        for (int i = 0; i < 16; ++i) a1[i] = 0u;
 #pragma unroll
-    for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? gs.cb.xs[p][j] : 0.0f);
-    set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);           // ones that pick up b_hi, b_mid, b_lo
-    set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
-    set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
+        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? gs.cb.xs[p][j] : 0.0f);
+        set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
+        set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
+        set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
+    }
 
     // prologue: layer-1 operands of the first tile of each slot
 #pragma unroll
     for (int s = 0; s < GSLOT; ++s) {
         if (s < n_tiles) {
-            const int t = s * tpt + sub;
-            put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
-            tmem_st16(tD0 + s * 128 + 64, a1);
-            tc_wait_st();
+            if (h == 0) {
+                const int t = s * tpt + sub;
+                put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
+                tmem_st16(tD0 + s * 128 + 64, a1);
+                tc_wait_st();
+            }
             tc_fence_before();
             mbar_arrive(&gs.bar_A[s]);
         }
@@ -390,38 +403,56 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     mbar_wait(&gs.bar_D[s], (phD >> s) & 1u);
                     phD ^= (1u << s);
                     tc_fence_after();
-                    uint32_t v[64];
-                    tmem_ld32(tD, v);
-                    tmem_ld32(tD + 32, v + 32);
+                    uint32_t v[NCOL];
+#pragma unroll
+                    for (int c = 0; c < NCOL / 32; ++c) tmem_ld32(tD + NCOL * h + 32 * c, v + 32 * c);
                     tc_wait_ld();
                     if (layer < MEMS_HIDDEN - 1) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
+                        for (int c = 0; c < NCOL / 32; ++c) {
                             uint32_t hi2[16], lo2[16];
                             epilogue_split(v + 32 * c, hi2, lo2);
-                            tmem_st16(tD + 64 + 16 * c, hi2);
-                            tmem_st16(tD + 96 + 16 * c, lo2);
+                            tmem_st16(tD + 64 + (NCOL / 2) * h + 16 * c, hi2);
+                            tmem_st16(tD + 96 + (NCOL / 2) * h + 16 * c, lo2);
                         }
                         tc_wait_st();
                         tc_fence_before();
                         mbar_arrive(&gs.bar_A[s]);
                     } else {
+                        uint64_t acc = pk(0.0f, 0.0f);
+#pragma unroll
+                        for (int c = 0; c < NCOL / 32; ++c) acc = epilogue_dot(v + 32 * c, sm.w7 + NCOL * h + 32 * c, acc);
                         float oa, ob;
-                        upk(epilogue_dot(v + 32, sm.w7 + 32, epilogue_dot(v, sm.w7, pk(0.0f, 0.0f))), oa, ob);
-                        const float o = (oa + ob) + sm.b7;
-                        const int t = tile * tpt + sub;
-                        if (chain_live && t < T) {
-                            if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
-                            const double r = s_yobs[t] - (double)o;
-                            Sp = fma(r, r, Sp);
+                        upk(acc, oa, ob);
+                        float o = oa + ob;
+                        if (NH == 2) {                 // the upper column half hands its partial dot to the lower one
+                            if (h == 1) {
+                                gs.xchg[s][row] = o;
+                                mbar_arrive(&gs.bar_X[s][q]);          // release: the store above is visible to the waiter
+                            } else {
+                                mbar_wait(&gs.bar_X[s][q], (phD >> (2 + s)) & 1u);   // bits 2,3 of phD: bar_X parity
+                                phD ^= (4u << s);
+                                o += gs.xchg[s][row];
+                            }
+                        }
+                        if (h == 0) {
+                            o += sm.b7;
+                            const int t = tile * tpt + sub;
+                            if (chain_live && t < T) {
+                                if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                                const double r = s_yobs[t] - (double)o;
+                                Sp = fma(r, r, Sp);
+                            }
                         }
                         // this slot's D and A are free again: stage the layer-1 operand of its next tile
                         const int nt = tile + GSLOT;
                         if (nt < n_tiles) {
-                            const int t2 = nt * tpt + sub;
-                            put_input<P>(a1, P, s_ts[t2 < T ? t2 : T - 1]);
-                            tmem_st16(tD + 64, a1);
-                            tc_wait_st();
+                            if (h == 0) {
+                                const int t2 = nt * tpt + sub;
+                                put_input<P>(a1, P, s_ts[t2 < T ? t2 : T - 1]);
+                                tmem_st16(tD + 64, a1);
+                                tc_wait_st();
+                            }
                             tc_fence_before();
                             mbar_arrive(&gs.bar_A[s]);
                         } else {
@@ -432,8 +463,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             }
         }
     }
-    gs.Spart[gt] = Sp;
-    group_bar_sync(g);
+    if (h == 0) gs.Spart[row] = Sp;
+    group_bar_sync<NH>(g);
     if (gt < nc) {
         double S = 0.0;                                // fixed order: time sub-rows ascending
         for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nc + gt];
@@ -444,18 +475,23 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
 __device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
+template <int NH>
 __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, double* s_yobs, float* s_ts) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     if (tid == 0) {
         for (int g = 0; g < NGROUP; ++g)
-            for (int s = 0; s < GSLOT; ++s) { mbar_init(&sm.grp[g].bar_A[s], GTHREADS); mbar_init(&sm.grp[g].bar_D[s], 1); }
+            for (int s = 0; s < GSLOT; ++s) {
+                mbar_init(&sm.grp[g].bar_A[s], gthreads(NH));
+                mbar_init(&sm.grp[g].bar_D[s], 1);
+                for (int q = 0; q < 4; ++q) mbar_init(&sm.grp[g].bar_X[s][q], 32);
+            }
         mbar_init(&sm.bar_w, 1);
         sm.c = pb.c;
         fence_barrier_init();
     }
     __syncthreads();
-    if (warp == NWORKER / 32) {
+    if (warp == nworker(NH) / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&sm.tmem_base)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -466,42 +502,44 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
             bulk_g2s(sm.w7, src + (size_t)NBLK * BLK, WIMG_TAIL, &sm.bar_w);
         }
     }
-    for (int i = tid; i < pb.c.T; i += NTHREADS) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+    for (int i = tid; i < pb.c.T; i += nthreads(NH)) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     mbar_wait(&sm.bar_w, 0);
 }
 
+template <int NH>
 __device__ __forceinline__ void tc_epilogue_free(TcSmem& sm) {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == NWORKER / 32) {
+    if ((threadIdx.x >> 5) == nworker(NH) / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(512) : "memory");
     }
 }
 
-template <int P>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int P, int NH>
+__global__ void __launch_bounds__(nthreads(NH), 1)
 tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
     float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
-    tc_prologue(sm, pb, s_yobs, s_ts);
+    tc_prologue<NH>(sm, pb, s_yobs, s_ts);
 
+    constexpr int NW = nworker(NH), GT = gthreads(NH);
     const int T = sm.c.T, nc = ra.nc, log2nc = ilog2(ra.nc);
     const int tid = threadIdx.x;
     const int nbatch = (ch.C + nc - 1) / nc;
     const int tpt = 128 >> log2nc;
     const int n_tiles = (T + tpt - 1) / tpt;
-    const int g = (tid < NWORKER) ? (tid >> 7) : ((tid - NWORKER) >> 5);
+    const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (tid >= NWORKER) {
+    if (tid >= NW) {
         if ((tid & 31) == 0) {
             uint32_t phA = 0;
             for (int batch = gid; batch < nbatch; batch += gstride)
@@ -509,27 +547,27 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
         }
         __syncwarp();
     } else {
-        const int gt = tid & (GTHREADS - 1);
+        const int gt = tid & (GT - 1);
         uint32_t phD = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, ch.C - c0);
-            group_bar_sync(g);
+            group_bar_sync<NH>(g);
             batch_load(gs.cb, ch, P, c0, gt, ncv);
             for (int s = 0; s < ra.n_steps; ++s) {
                 if (gt < ncv) batch_propose(gs.cb, sm.c, ch, ra, c0, gt, s);
-                group_bar_sync(g);
-                tc_eval_group<P>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phD);
+                group_bar_sync<NH>(g);
+                tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phD);
                 if (gt < ncv) batch_finish(gs.cb, sm.c, ch, ra, c0, gt, s, gs.Spart[gt]);
             }
             batch_store(gs.cb, ch, P, c0, gt, ncv);
         }
     }
-    tc_epilogue_free(sm);
+    tc_epilogue_free<NH>(sm);
 }
 
-template <int P>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int P, int NH>
+__global__ void __launch_bounds__(nthreads(NH), 1)
 tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict__ x, int n, int nc, float* y_out,
                   double* ll_out, int apply_prior) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -537,30 +575,31 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const MemsProblem& pb = *pbp;
     double* s_yobs = reinterpret_cast<double*>(smem_raw + sizeof(TcSmem));
     float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
-    tc_prologue(sm, pb, s_yobs, s_ts);
+    tc_prologue<NH>(sm, pb, s_yobs, s_ts);
 
+    constexpr int NW = nworker(NH), GT = gthreads(NH);
     const int T = sm.c.T, log2nc = ilog2(nc);
     const int tid = threadIdx.x;
     const int nbatch = (n + nc - 1) / nc;
     const int tpt = 128 >> log2nc;
     const int n_tiles = (T + tpt - 1) / tpt;
-    const int g = (tid < NWORKER) ? (tid >> 7) : ((tid - NWORKER) >> 5);
+    const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (tid >= NWORKER) {
+    if (tid >= NW) {
         if ((tid & 31) == 0) {
             uint32_t phA = 0;
             for (int batch = gid; batch < nbatch; batch += gstride) mma_serve_eval(sm, gs, g, n_tiles, phA);
         }
         __syncwarp();
     } else {
-        const int gt = tid & (GTHREADS - 1);
+        const int gt = tid & (GT - 1);
         uint32_t phD = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, n - c0);
-            group_bar_sync(g);
+            group_bar_sync<NH>(g);
             if (gt < ncv) {
                 bool inb = true;
                 for (int p = 0; p < P; ++p) {
@@ -570,15 +609,15 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
                 }
                 gs.cb.inb[gt] = inb ? 1 : 0;
             }
-            group_bar_sync(g);
-            tc_eval_group<P>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phD);
+            group_bar_sync<NH>(g);
+            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phD);
             if (gt < ncv && ll_out) {
                 const double ll = sm.c.neg_half_inv_sigma2 * gs.Spart[gt];
                 ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
             }
         }
     }
-    tc_epilogue_free(sm);
+    tc_epilogue_free<NH>(sm);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -705,22 +744,30 @@ inline void put(unsigned char* img, int blk, int row, int k, double v) {
     memcpy(img + off, &b, 2);
 }
 
-#define MEMS_LAUNCH_P(KERNEL, Pv, grid, smem, st, ...)                                                         \
-    do {                                                                                                      \
-        cudaError_t e_;                                                                                       \
-        switch (Pv) {                                                                                         \
-            case 1: e_ = cudaFuncSetAttribute(KERNEL<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
-                if (e_ == cudaSuccess) KERNEL<1><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
-            case 2: e_ = cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
-                if (e_ == cudaSuccess) KERNEL<2><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
-            case 3: e_ = cudaFuncSetAttribute(KERNEL<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
-                if (e_ == cudaSuccess) KERNEL<3><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
-            default: e_ = cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)); \
-                if (e_ == cudaSuccess) KERNEL<4><<<grid, NTHREADS, smem, st>>>(__VA_ARGS__); break;          \
-        }                                                                                                     \
-        if (e_ != cudaSuccess) return (int)e_;                                                                \
-        return (int)cudaGetLastError();                                                                       \
-    } while (0)
+template <int NH, typename K1, typename K2, typename K3, typename K4, typename... Args>
+int launch_by_p(int Pv, K1 k1, K2 k2, K3 k3, K4 k4, int grid, size_t smem, cudaStream_t st, Args... args) {
+    auto go = [&](auto k) -> int {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        k<<<grid, nthreads(NH), smem, st>>>(args...);
+        return (int)cudaGetLastError();
+    };
+    switch (Pv) {
+        case 1: return go(k1);
+        case 2: return go(k2);
+        case 3: return go(k3);
+        default: return go(k4);
+    }
+}
+
+int g_tc_variant = -1;   // -1: read MEMS_TC_NH from the environment once
+int tc_nh() {
+    if (g_tc_variant < 0) {
+        const char* e = getenv("MEMS_TC_NH");
+        g_tc_variant = (e && e[0] == '1') ? 1 : 2;
+    }
+    return g_tc_variant;
+}
 
 }  // namespace
 
@@ -796,7 +843,11 @@ int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
     const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
     const int want = (nbatch + NGROUP - 1) / NGROUP;
     const int grid = want < ctx.sm_count ? want : ctx.sm_count;
-    MEMS_LAUNCH_P(tc_run_kernel, ctx.pb_host->c.P, grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
+    if (tc_nh() == 1)
+        return launch_by_p<1>(ctx.pb_host->c.P, tc_run_kernel<1, 1>, tc_run_kernel<2, 1>, tc_run_kernel<3, 1>, tc_run_kernel<4, 1>,
+                              grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
+    return launch_by_p<2>(ctx.pb_host->c.P, tc_run_kernel<1, 2>, tc_run_kernel<2, 2>, tc_run_kernel<3, 2>, tc_run_kernel<4, 2>,
+                          grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
 }
 
 int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
@@ -806,8 +857,12 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
     const int nbatch = (n + nc - 1) / nc;
     const int want = (nbatch + NGROUP - 1) / NGROUP;
     const int grid = want < ctx.sm_count ? want : ctx.sm_count;
-    MEMS_LAUNCH_P(tc_forward_kernel, ctx.pb_host->c.P, (grid > 0 ? grid : 1), smem, ctx.stream, ctx.pb_dev, x_dev, n, nc,
-                  y_out, ll_out, apply_prior);
+    const int gr = grid > 0 ? grid : 1;
+    if (tc_nh() == 1)
+        return launch_by_p<1>(ctx.pb_host->c.P, tc_forward_kernel<1, 1>, tc_forward_kernel<2, 1>, tc_forward_kernel<3, 1>,
+                              tc_forward_kernel<4, 1>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior);
+    return launch_by_p<2>(ctx.pb_host->c.P, tc_forward_kernel<1, 2>, tc_forward_kernel<2, 2>, tc_forward_kernel<3, 2>,
+                          tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior);
 }
 
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st) {
