@@ -86,6 +86,23 @@ int  mems_set_problem(mems_handle_t h, const double* time, const double* scaler_
 int  mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out,
                   double* loglik_out, void* stream);
 
+/* Sampler variant (default MEMS_SAMPLER_MH = the reference's sampler).  The two others have NO
+ * implementation or artefact in the reference; they follow cuqi.sampler.CWMH
+ * semantics and Christen & Fox (2005):
+ *   CWMH: per update draw x_o = x + scale (.) z once, then for p = 0..P-1 replace component p,
+ *         score, accept with its own uniform -- P surrogate passes per update; cw_scale[P] (HOST)
+ *         is the initial per-component proposal std; adaptation target 0.21/P + 0.23.
+ *   DA:   stage 1 scores every da_stride-th time point (log-likelihood rescaled by T/Tc) and promotes
+ *         with log u1 <= min(0, lc* - lc); stage 2 (promoted only) scores all T points and accepts
+ *         with log u2 <= min(0, (l* - l) - (lc* - lc)).  A pass no chain of a batch needs is skipped.
+ * Call before mems_init_chains.  With n_sub = 1 (MH), P (CWMH), 2 (DA) the per-update arrays of
+ * mems_run_explicit / mems_draw become log_u [n_steps][n_sub][C], loglik_prop_out and
+ * decisions_out [n_steps][n_sub][C]; for CWMH xi holds the standard normals z, not chol*z. */
+#define MEMS_SAMPLER_MH   0
+#define MEMS_SAMPLER_CWMH 1
+#define MEMS_SAMPLER_DA   2
+int  mems_set_sampler(mems_handle_t h, int32_t sampler, const double* cw_scale, int32_t da_stride);
+
 /* Chain initialisation.  Replaces MH(target, proposal, x0) + the first lines of
  * cuqi MH._sample_adapt (samples[:,0]=x0, target_eval[0]=logd(x0), acc[0]=1, scale=0.1):
  * x0_dev [P][C] (device, f64); scale0 = initial proposal scale; seed = Philox key.
@@ -124,6 +141,11 @@ int  mems_draw(mems_handle_t h, uint64_t step0, int32_t n_steps, double* xi_out,
  * initial acc[0]=1 not included), steps_done (HOST pointer, synchronises the stream). */
 int  mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale,
                     uint32_t* accept_count, uint64_t* steps_done, void* stream);
+
+/* Variant-specific state (device pointers, each may be NULL): scale_cw [P][C] f64 (CWMH),
+ * loglik_coarse [C] f64 and promote_count [C] u32 (DA). */
+int  mems_get_aux(mems_handle_t h, double* scale_cw, double* loglik_coarse, uint32_t* promote_count,
+                  void* stream);
 
 /* Generic Dense-stack inference.  Replaces NN_Model.predict / nn_model.model(X)
  * (src/SurrogateModeling/model.py:142-151, src/InverseProblems/utils.py:39) for any of the

@@ -17,11 +17,14 @@ MEMS_WIDTH = 64
 MEMS_HIDDEN = 6
 PATH_FP32 = 0
 PATH_TC = 1
+SAMPLER_MH = 0
+SAMPLER_CWMH = 1
+SAMPLER_DA = 2
 
 EXPORTS = [
     "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
     "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
-    "mems_draw", "mems_get_state", "mems_mlp_forward", "mems_launch_count", "mems_selftest_umma",
+    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_launch_count", "mems_selftest_umma",
 ]
 
 
@@ -63,6 +66,8 @@ def lib():
     L.mems_run_explicit.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mems_draw.argtypes = [vp, u64, i32, vp, vp, vp]
     L.mems_get_state.argtypes = [vp, vp, vp, vp, vp, C.POINTER(u64), vp]
+    L.mems_get_aux.argtypes = [vp, vp, vp, vp, vp]
+    L.mems_set_sampler.argtypes = [vp, i32, vp, i32]
     L.mems_mlp_forward.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), vp, i64, vp, vp]
     L.mems_launch_count.argtypes = [vp]
     L.mems_launch_count.restype = i64

@@ -46,6 +46,9 @@ struct MemsHandle_ {
     void* dev_wimg = nullptr;
     MemsChains chains;
     bool have_weights = false, have_problem = false, have_chains = false;
+    int sampler = MEMS_MODE_RW;
+    int da_stride = 4;
+    double cw_scale[MEMS_PMAX] = {1.0, 1.0, 1.0, 1.0};
     unsigned long long steps_done = 0;
     long long launches = 0;
 };
@@ -133,7 +136,12 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
               cudaMalloc(&h->chains.lambda, sizeof(double) * C) == cudaSuccess &&
               cudaMalloc(&h->chains.win_acc, sizeof(int) * C) == cudaSuccess &&
               cudaMalloc(&h->chains.adapt_i, sizeof(int) * C) == cudaSuccess &&
-              cudaMalloc(&h->chains.acc_count, sizeof(unsigned int) * C) == cudaSuccess;
+              cudaMalloc(&h->chains.acc_count, sizeof(unsigned int) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.scale_cw, sizeof(double) * P * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.lambda_cw, sizeof(double) * P * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.win_cw, sizeof(int) * P * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.llc, sizeof(double) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.prom_count, sizeof(unsigned int) * C) == cudaSuccess;
     if (!ok) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
         mems_destroy(h);
@@ -149,6 +157,8 @@ void mems_destroy(mems_handle_t h) {
     cudaFree(h->dev_pb); cudaFree(h->dev_ts); cudaFree(h->dev_yobs); cudaFree(h->dev_wimg);
     cudaFree(h->chains.x); cudaFree(h->chains.ll); cudaFree(h->chains.scale); cudaFree(h->chains.lambda);
     cudaFree(h->chains.win_acc); cudaFree(h->chains.adapt_i); cudaFree(h->chains.acc_count);
+    cudaFree(h->chains.scale_cw); cudaFree(h->chains.lambda_cw); cudaFree(h->chains.win_cw);
+    cudaFree(h->chains.llc); cudaFree(h->chains.prom_count);
     delete h;
 }
 
@@ -212,25 +222,52 @@ int mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out, 
     if (!x_dev) return fail(MEMS_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     MemsLaunchCtx ctx = make_ctx(h, stream);
-    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, x_dev, n, y_out, loglik_out, 0)
-                                                : mems_fp32_forward(ctx, x_dev, n, y_out, loglik_out, 0);
+    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, x_dev, n, y_out, loglik_out, 0, 1)
+                                                : mems_fp32_forward(ctx, x_dev, n, y_out, loglik_out, 0, 1);
     h->launches += 1;
     if (e != 0) return fail(MEMS_E_CUDA, "forward launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return MEMS_OK;
 }
 
 namespace {
-__global__ void init_chains_kernel(MemsChains ch, int P, const double* x0, double scale0) {
+struct CwInit { double s[MEMS_PMAX]; };
+__global__ void init_chains_kernel(MemsChains ch, int P, const double* x0, double scale0, CwInit cw) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ch.C) return;
-    for (int p = 0; p < P; ++p) ch.x[(size_t)p * ch.C + c] = x0[(size_t)p * ch.C + c];
+    for (int p = 0; p < P; ++p) {
+        ch.x[(size_t)p * ch.C + c] = x0[(size_t)p * ch.C + c];
+        ch.scale_cw[(size_t)p * ch.C + c] = cw.s[p];
+        ch.lambda_cw[(size_t)p * ch.C + c] = cw.s[p];
+        ch.win_cw[(size_t)p * ch.C + c] = 1;   // cuqi CWMH: acc[:, 0] = 1
+    }
     ch.scale[c] = scale0;
     ch.lambda[c] = scale0;
     ch.win_acc[c] = 1;          // cuqi: acc[0] = 1 belongs to the first adaptation window
     ch.adapt_i[c] = 0;
     ch.acc_count[c] = 0u;
+    ch.prom_count[c] = 0u;
 }
 }  // namespace
+
+int mems_set_sampler(mems_handle_t h, int32_t sampler, const double* cw_scale, int32_t da_stride) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (sampler != MEMS_MODE_RW && sampler != MEMS_MODE_CW && sampler != MEMS_MODE_DA)
+        return fail(MEMS_E_INVALID, "unknown sampler %d", sampler);
+    if (sampler == MEMS_MODE_CW) {
+        if (!cw_scale) return fail(MEMS_E_INVALID, "component-wise MH needs cw_scale[P]");
+        for (int p = 0; p < h->host_pb.c.P; ++p) {
+            if (!(cw_scale[p] >= 0.0)) return fail(MEMS_E_INVALID, "cw_scale[%d] must be >= 0", p);
+            h->cw_scale[p] = cw_scale[p];
+        }
+    }
+    if (sampler == MEMS_MODE_DA) {
+        if (da_stride < 1 || da_stride > h->host_pb.c.T) return fail(MEMS_E_INVALID, "da_stride=%d outside [1,T]", da_stride);
+        h->da_stride = da_stride;
+    }
+    h->sampler = sampler;
+    h->have_chains = false;     // chains must be (re)initialised for the new sampler
+    return MEMS_OK;
+}
 
 int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint64_t seed, uint64_t chain_id0,
                      void* stream) {
@@ -243,13 +280,21 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
     h->steps_done = 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int C = h->chains.C;
-    init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.c.P, x0_dev, scale0);
+    CwInit cw;
+    for (int p = 0; p < MEMS_PMAX; ++p) cw.s[p] = h->cw_scale[p];
+    init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.c.P, x0_dev, scale0, cw);
     CUDA_TRY(cudaGetLastError());
     MemsLaunchCtx ctx = make_ctx(h, stream);
+    const bool tc = h->cfg.path == MEMS_PATH_TC;
     // target_eval[0] = logd(x0): likelihood + prior (-inf outside the box)
-    const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1)
-                                                : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1);
+    int e = tc ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1, 1)
+               : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1, 1);
     h->launches += 2;
+    if (e == 0 && h->sampler == MEMS_MODE_DA) {   // coarse log-likelihood of the start state
+        e = tc ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride)
+               : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride);
+        h->launches += 1;
+    }
     if (e != 0) return fail(MEMS_E_CUDA, "init launch failed: %s", cudaGetErrorString((cudaError_t)e));
     h->have_chains = true;
     return MEMS_OK;
@@ -259,6 +304,10 @@ static int run_common(mems_handle_t h, MemsRunArgs& ra, void* stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     ra.step0 = h->steps_done;
     ra.nc = choose_nc(h, h->chains.C);
+    ra.mode = h->sampler;
+    ra.n_sub = (h->sampler == MEMS_MODE_CW) ? h->host_pb.c.P : (h->sampler == MEMS_MODE_DA ? 2 : 1);
+    ra.da_stride = h->da_stride;
+    ra.target_acc = (h->sampler == MEMS_MODE_CW) ? 0.21 / h->host_pb.c.P + 0.23 : 0.234;
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_run(ctx, ra) : mems_fp32_run(ctx, ra);
     h->launches += 1;
@@ -295,12 +344,13 @@ int mems_run_explicit(mems_handle_t h, int32_t n_steps, int32_t adapt_window, co
 }
 
 int mems_draw(mems_handle_t h, uint64_t step0, int32_t n_steps, double* xi_out, double* log_u_out, void* stream) {
+    const int n_sub = !h ? 1 : (h->sampler == MEMS_MODE_CW) ? h->host_pb.c.P : (h->sampler == MEMS_MODE_DA ? 2 : 1);
     if (!h) return fail(MEMS_E_INVALID, "null handle");
     if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
     if (n_steps <= 0) return MEMS_OK;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     MemsLaunchCtx ctx = make_ctx(h, stream);
-    const int e = mems_draw_launch(ctx, step0, n_steps, xi_out, log_u_out);
+    const int e = mems_draw_launch(ctx, h->sampler, n_sub, step0, n_steps, xi_out, log_u_out);
     h->launches += 1;
     if (e != 0) return fail(MEMS_E_CUDA, "draw launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return MEMS_OK;
@@ -322,6 +372,19 @@ int mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale, ui
         CUDA_TRY(cudaStreamSynchronize(st));
         *steps_done = h->steps_done;
     }
+    return MEMS_OK;
+}
+
+int mems_get_aux(mems_handle_t h, double* scale_cw, double* loglik_coarse, uint32_t* promote_count, void* stream) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.c.P;
+    if (scale_cw) CUDA_TRY(cudaMemcpyAsync(scale_cw, h->chains.scale_cw, sizeof(double) * P * C, cudaMemcpyDeviceToDevice, st));
+    if (loglik_coarse) CUDA_TRY(cudaMemcpyAsync(loglik_coarse, h->chains.llc, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+    if (promote_count)
+        CUDA_TRY(cudaMemcpyAsync(promote_count, h->chains.prom_count, sizeof(unsigned int) * C, cudaMemcpyDeviceToDevice, st));
     return MEMS_OK;
 }
 

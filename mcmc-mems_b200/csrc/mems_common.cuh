@@ -48,24 +48,37 @@ struct MemsChains {
     int C;
     double* x;            // [P][C]
     double* ll;           // [C] log-likelihood core (-0.5*S/sigma2), -inf outside the prior box
-    double* scale;        // [C] cuqi self.scale
+    double* scale;        // [C] cuqi self.scale (random-walk MH / delayed acceptance)
     double* lambda;       // [C] cuqi lambd
     int* win_acc;         // [C] accepted updates in the open adaptation window
     int* adapt_i;         // [C] adaptation counter i
     unsigned int* acc_count;  // [C]
+    double* scale_cw;     // [P][C] component-wise MH: per-component proposal std
+    double* lambda_cw;    // [P][C]
+    int* win_cw;          // [P][C]
+    double* llc;          // [C] delayed acceptance: coarse log-likelihood of the current state
+    unsigned int* prom_count;  // [C] delayed acceptance: proposals promoted to the fine stage
     unsigned long long seed;
     unsigned long long chain_id0;
 };
 
+#define MEMS_MODE_RW 0     // random-walk MH            (cuqi.sampler.MH; the reference's sampler)
+#define MEMS_MODE_CW 1     // component-wise MH         (cuqi.sampler.CWMH semantics; unpinned)
+#define MEMS_MODE_DA 2     // delayed acceptance        (Christen & Fox 2005; unpinned)
+
 struct MemsRunArgs {
     int n_steps, adapt_window, thin;
+    int mode;                          // MEMS_MODE_*
+    int n_sub;                         // surrogate evaluations per update: 1 (RW), P (CW), 2 (DA)
+    int da_stride;                     // DA: the coarse stage scores every da_stride-th time point
+    double target_acc;                 // adaptation target: 0.234 (RW), 0.21/P + 0.23 (CW)
     unsigned long long step0;          // updates already done (global sample index of the state)
-    const double* xi;                  // explicit mode: [n_steps][P][C], else nullptr
-    const double* log_u;               // explicit mode: [n_steps][C]
+    const double* xi;                  // explicit mode: [n_steps][P][C] (RW/DA: chol*z; CW: z), else nullptr
+    const double* log_u;               // explicit mode: [n_steps][n_sub][C]
     double* samples_out;               // [n_keep][P][C] or nullptr
     double* loglik_out;                // [n_keep][C] or nullptr
-    double* llprop_out;                // explicit mode: [n_steps][C] or nullptr
-    unsigned char* decisions_out;      // explicit mode: [n_steps][C] or nullptr
+    double* llprop_out;                // explicit mode: [n_steps][n_sub][C] or nullptr
+    unsigned char* decisions_out;      // explicit mode: [n_steps][n_sub][C] or nullptr
     int nc;                            // chains per block batch (power of two <= MEMS_NCMAX)
 };
 
@@ -99,27 +112,31 @@ __device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, doubl
     z1 = (double)(r * s);
 }
 
-// The randomness of update `step` of global chain `gid`: xi = chol*z (P values) and log u.
-// purpose 0: normals 0..3; purpose 1: word x = uniform of the accept test (words y,z,w reserved
-// for second-stage / per-component uniforms).
-__device__ __forceinline__ void draw_update(const MemsConsts& pb, unsigned long long seed,
-                                            unsigned long long gid, unsigned long long step,
-                                            double* xi, double& log_u) {
+// The randomness of update `step` of global chain `gid`: four standard normals (Philox purpose 0)
+// and four log-uniforms (purpose 1).  RW/DA use xi = chol*z and log_u[0] (DA: also log_u[1] for
+// the second stage); CW uses z[p] and log_u[p] for component p.
+__device__ __forceinline__ void draw_raw(unsigned long long seed, unsigned long long gid, unsigned long long step,
+                                         double* z, double* log_u) {
     const unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
     const unsigned int c0 = (unsigned int)gid, c1 = (unsigned int)(gid >> 32);
     const unsigned int c2 = (unsigned int)step, c3 = (unsigned int)(step >> 32) & 0x00FFFFFFu;
     const Philox4 n = philox4x32_10(c0, c1, c2, c3, k0, k1);
     const Philox4 u = philox4x32_10(c0, c1, c2, c3 | (1u << 24), k0, k1);
-    double z[4];
     box_muller(n.x, n.y, z[0], z[1]);
     box_muller(n.z, n.w, z[2], z[3]);
+    log_u[0] = log(((double)u.x + 1.0) * 2.3283064365386963e-10);   // u in (0, 1]
+    log_u[1] = log(((double)u.y + 1.0) * 2.3283064365386963e-10);
+    log_u[2] = log(((double)u.z + 1.0) * 2.3283064365386963e-10);
+    log_u[3] = log(((double)u.w + 1.0) * 2.3283064365386963e-10);
+}
+
+__device__ __forceinline__ void chol_mul(const MemsConsts& pb, const double* z, double* xi) {
     const int P = pb.P;
     for (int p = 0; p < P; ++p) {
         double acc = 0.0;
         for (int q = 0; q <= p; ++q) acc = fma(pb.chol[p * P + q], z[q], acc);
         xi[p] = acc;
     }
-    log_u = log(((double)u.x + 1.0) * 2.3283064365386963e-10);      // u in (0, 1]
 }
 
 // cuqi MH.single_update acceptance rule; min(0, NaN) == 0 in Python is reproduced.
@@ -135,18 +152,26 @@ __device__ __forceinline__ bool mh_accept(double log_u, double ll_star, double l
 struct ChainBatch {
     double x[MEMS_PMAX][MEMS_NCMAX];      // current state
     double xp[MEMS_PMAX][MEMS_NCMAX];     // proposal
+    double z[MEMS_PMAX][MEMS_NCMAX];      // CW: the step's normals (x_o = x + scale (.) z is drawn once per step)
+    double lu[MEMS_PMAX][MEMS_NCMAX];     // log-uniforms of the step (RW: [0]; DA: [0],[1]; CW: [component])
+    double scale_cw[MEMS_PMAX][MEMS_NCMAX];
+    double lambda_cw[MEMS_PMAX][MEMS_NCMAX];
     double ll[MEMS_NCMAX];
     double scale[MEMS_NCMAX];
     double lambda[MEMS_NCMAX];
-    double logu[MEMS_NCMAX];
+    double llc[MEMS_NCMAX];               // DA: coarse log-likelihood of the current state
+    double llc_star[MEMS_NCMAX];          // DA: coarse log-likelihood of the proposal
     float xs[MEMS_PMAX][MEMS_NCMAX];      // scaled proposal, f32 network input
+    int win_cw[MEMS_PMAX][MEMS_NCMAX];
     int win_acc[MEMS_NCMAX];
     int adapt_i[MEMS_NCMAX];
     unsigned int acc_count[MEMS_NCMAX];
+    unsigned int prom_count[MEMS_NCMAX];
     unsigned char inb[MEMS_NCMAX];        // proposal inside the prior box
+    unsigned char live[MEMS_NCMAX];       // rows of this chain must be evaluated in the coming pass
 };
 
-__device__ __forceinline__ void batch_load(ChainBatch& cb, const MemsChains& ch, int P, int c0, int j, int ncv) {
+__device__ __forceinline__ void batch_load(ChainBatch& cb, const MemsChains& ch, int P, int mode, int c0, int j, int ncv) {
     if (j < ncv) {
         const int c = c0 + j;
         for (int p = 0; p < P; ++p) cb.x[p][j] = ch.x[(size_t)p * ch.C + c];
@@ -156,10 +181,21 @@ __device__ __forceinline__ void batch_load(ChainBatch& cb, const MemsChains& ch,
         cb.win_acc[j] = ch.win_acc[c];
         cb.adapt_i[j] = ch.adapt_i[c];
         cb.acc_count[j] = ch.acc_count[c];
+        if (mode == MEMS_MODE_CW) {
+            for (int p = 0; p < P; ++p) {
+                cb.scale_cw[p][j] = ch.scale_cw[(size_t)p * ch.C + c];
+                cb.lambda_cw[p][j] = ch.lambda_cw[(size_t)p * ch.C + c];
+                cb.win_cw[p][j] = ch.win_cw[(size_t)p * ch.C + c];
+            }
+        }
+        if (mode == MEMS_MODE_DA) {
+            cb.llc[j] = ch.llc[c];
+            cb.prom_count[j] = ch.prom_count[c];
+        }
     }
 }
 
-__device__ __forceinline__ void batch_store(const ChainBatch& cb, const MemsChains& ch, int P, int c0, int j, int ncv) {
+__device__ __forceinline__ void batch_store(const ChainBatch& cb, const MemsChains& ch, int P, int mode, int c0, int j, int ncv) {
     if (j < ncv) {
         const int c = c0 + j;
         for (int p = 0; p < P; ++p) ch.x[(size_t)p * ch.C + c] = cb.x[p][j];
@@ -169,6 +205,17 @@ __device__ __forceinline__ void batch_store(const ChainBatch& cb, const MemsChai
         ch.win_acc[c] = cb.win_acc[j];
         ch.adapt_i[c] = cb.adapt_i[j];
         ch.acc_count[c] = cb.acc_count[j];
+        if (mode == MEMS_MODE_CW) {
+            for (int p = 0; p < P; ++p) {
+                ch.scale_cw[(size_t)p * ch.C + c] = cb.scale_cw[p][j];
+                ch.lambda_cw[(size_t)p * ch.C + c] = cb.lambda_cw[p][j];
+                ch.win_cw[(size_t)p * ch.C + c] = cb.win_cw[p][j];
+            }
+        }
+        if (mode == MEMS_MODE_DA) {
+            ch.llc[c] = cb.llc[j];
+            ch.prom_count[c] = cb.prom_count[j];
+        }
     }
 }
 
@@ -178,66 +225,172 @@ __device__ __forceinline__ float scale_param(const MemsConsts& pb, int p, double
     return (float)((v - pb.mean[p]) / pb.sscale[p]);
 }
 
-// Thread j proposes for chain c0+j at local update index s (global index step0+s).
-__device__ __forceinline__ void batch_propose(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
-                                              const MemsRunArgs& ra, int c0, int j, int s) {
-    const int P = pb.P;
-    const int c = c0 + j;
-    double xi[MEMS_PMAX];
-    double lu;
-    if (ra.xi != nullptr) {
-        for (int p = 0; p < P; ++p) xi[p] = ra.xi[((size_t)s * P + p) * ch.C + c];
-        lu = ra.log_u[(size_t)s * ch.C + c];
-    } else {
-        draw_update(pb, ch.seed, ch.chain_id0 + (unsigned long long)c, ra.step0 + (unsigned long long)s, xi, lu);
-    }
-    const double sc = cb.scale[j];
+// Publish proposal xp[.][j] as network input + prior-box flag.
+__device__ __forceinline__ void batch_publish(ChainBatch& cb, const MemsConsts& pb, int j) {
     bool inb = true;
-    for (int p = 0; p < P; ++p) {
-        // two roundings like numpy's `x_t + self.scale*xi` (no FMA contraction): keeps states bit-exact
-        const double v = __dadd_rn(cb.x[p][j], __dmul_rn(sc, xi[p]));
-        cb.xp[p][j] = v;
+    for (int p = 0; p < pb.P; ++p) {
+        const double v = cb.xp[p][j];
         cb.xs[p][j] = scale_param(pb, p, v);
         inb = inb && !(v < pb.low[p]) && !(v > pb.high[p]);
     }
     cb.inb[j] = inb ? 1 : 0;
-    cb.logu[j] = lu;
+    cb.live[j] = inb ? 1 : 0;
 }
 
-// Thread j finishes update s of chain c0+j given S = sum_t (y_obs - f(x*))^2.
-__device__ __forceinline__ void batch_finish(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
-                                             const MemsRunArgs& ra, int c0, int j, int s, double S) {
+// Before surrogate pass `sub` of update s: thread j prepares the proposal of chain c0+j.
+// Time stride of the coming pass is returned by batch_pass_stride().
+__device__ __forceinline__ void batch_pre(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
+                                          const MemsRunArgs& ra, int c0, int j, int s, int sub) {
     const int P = pb.P;
     const int c = c0 + j;
-    const double ll_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S : -CUDART_INF;
-    const bool acc = mh_accept(cb.logu[j], ll_star, cb.ll[j]);
-    if (acc) {
-        for (int p = 0; p < P; ++p) cb.x[p][j] = cb.xp[p][j];
-        cb.ll[j] = ll_star;
-        cb.acc_count[j] += 1u;
+    if (sub == 0) {                                    // the step's randomness
+        double z[4], lu[4];
+        if (ra.xi != nullptr) {
+            for (int p = 0; p < P; ++p) z[p] = ra.xi[((size_t)s * P + p) * ch.C + c];
+            for (int k = 0; k < ra.n_sub; ++k) lu[k] = ra.log_u[((size_t)s * ra.n_sub + k) * ch.C + c];
+        } else {
+            draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, ra.step0 + (unsigned long long)s, z, lu);
+            if (ra.mode != MEMS_MODE_CW) {
+                double xi[MEMS_PMAX];
+                chol_mul(pb, z, xi);
+                for (int p = 0; p < P; ++p) z[p] = xi[p];
+            }
+        }
+        for (int p = 0; p < P; ++p) cb.z[p][j] = z[p];
+        for (int k = 0; k < ra.n_sub; ++k) cb.lu[k][j] = lu[k];
     }
-    // cuqi MH._sample_adapt: the window closed at (s+1) % Na == 0 holds acc[idx:idx+Na], i.e. it
-    // excludes the decision just taken, which opens the next window.
-    const unsigned long long k = ra.step0 + (unsigned long long)s + 1ull;   // global sample index
-    if (ra.adapt_window > 0 && (k % (unsigned long long)ra.adapt_window) == 0ull) {
-        const double hat = (double)cb.win_acc[j] / (double)ra.adapt_window;
-        const double zeta = 1.0 / sqrt((double)(cb.adapt_i[j] + 1));
-        const double lam = exp(log(cb.lambda[j]) + zeta * (hat - 0.234));
-        cb.lambda[j] = lam;
-        cb.scale[j] = fmin(lam, 1.0);
-        cb.adapt_i[j] += 1;
-        cb.win_acc[j] = 0;
+    if (ra.mode == MEMS_MODE_CW) {
+        // cuqi CWMH.single_update: x_o = x_t + scale (.) z is fixed at the start of the step; pass `sub`
+        // replaces component `sub` of the CURRENT state (earlier components may already have moved).
+        for (int p = 0; p < P; ++p) cb.xp[p][j] = cb.x[p][j];
+        if (sub == 0)                                     // remember x_o in z[]: x_o[p] = x[p] + scale[p]*z[p]
+            for (int p = 0; p < P; ++p) cb.z[p][j] = __dadd_rn(cb.x[p][j], __dmul_rn(cb.scale_cw[p][j], cb.z[p][j]));
+        cb.xp[sub][j] = cb.z[sub][j];
+        batch_publish(cb, pb, j);
+    } else if (sub == 0) {
+        // two roundings like numpy's `x_t + self.scale*xi` (no FMA contraction): keeps states bit-exact
+        const double sc = cb.scale[j];
+        for (int p = 0; p < P; ++p) cb.xp[p][j] = __dadd_rn(cb.x[p][j], __dmul_rn(sc, cb.z[p][j]));
+        batch_publish(cb, pb, j);
     }
-    cb.win_acc[j] += acc ? 1 : 0;
-    if (ra.xi != nullptr) {                         // parity mode: everything, every update
-        if (ra.llprop_out) ra.llprop_out[(size_t)s * ch.C + c] = ll_star;
-        if (ra.decisions_out) ra.decisions_out[(size_t)s * ch.C + c] = acc ? 1 : 0;
-    }
+    // DA, sub == 1: xs unchanged; live[] was set by the first-stage decision
+}
+
+__device__ __forceinline__ int batch_pass_stride(const MemsRunArgs& ra, int sub) {
+    return (ra.mode == MEMS_MODE_DA && sub == 0) ? ra.da_stride : 1;
+}
+
+// cuqi vanishing adaptation (MH._sample_adapt / CWMH._sample_adapt): lambda <- exp(log lambda + (hat - star)/sqrt(i+1))
+__device__ __forceinline__ double adapt_lambda(double lambda, int win, int Na, int i, double star) {
+    const double hat = (double)win / (double)Na;
+    const double zeta = 1.0 / sqrt((double)(i + 1));
+    return exp(log(lambda) + zeta * (hat - star));
+}
+
+__device__ __forceinline__ void batch_outputs(const ChainBatch& cb, const MemsChains& ch, const MemsRunArgs& ra,
+                                              int P, int c, int j, int s) {
     if (((s + 1) % ra.thin) == 0) {
         const size_t row = (size_t)((s + 1) / ra.thin - 1);
         if (ra.samples_out)
             for (int p = 0; p < P; ++p) ra.samples_out[(row * P + p) * ch.C + c] = cb.x[p][j];
         if (ra.loglik_out) ra.loglik_out[row * ch.C + c] = cb.ll[j];
+    }
+}
+
+// After surrogate pass `sub` of update s: thread j consumes S = sum_t (y_obs - f(x*))^2 (over the pass's time points).
+__device__ __forceinline__ void batch_post(ChainBatch& cb, const MemsConsts& pb, const MemsChains& ch,
+                                           const MemsRunArgs& ra, int c0, int j, int s, int sub, double S) {
+    const int P = pb.P;
+    const int c = c0 + j;
+    const unsigned long long k = ra.step0 + (unsigned long long)s + 1ull;   // global sample index
+    const bool adapt_now = ra.adapt_window > 0 && (k % (unsigned long long)ra.adapt_window) == 0ull;
+    const size_t orow = ((size_t)s * ra.n_sub + sub) * ch.C + c;
+    if (ra.mode == MEMS_MODE_RW) {
+        const double ll_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S : -CUDART_INF;
+        const bool acc = mh_accept(cb.lu[0][j], ll_star, cb.ll[j]);
+        if (acc) {
+            for (int p = 0; p < P; ++p) cb.x[p][j] = cb.xp[p][j];
+            cb.ll[j] = ll_star;
+            cb.acc_count[j] += 1u;
+        }
+        // cuqi MH._sample_adapt: the window closed at (s+1) % Na == 0 holds acc[idx:idx+Na], i.e. it
+        // excludes the decision just taken, which opens the next window.
+        if (adapt_now) {
+            const double lam = adapt_lambda(cb.lambda[j], cb.win_acc[j], ra.adapt_window, cb.adapt_i[j], ra.target_acc);
+            cb.lambda[j] = lam;
+            cb.scale[j] = fmin(lam, 1.0);
+            cb.adapt_i[j] += 1;
+            cb.win_acc[j] = 0;
+        }
+        cb.win_acc[j] += acc ? 1 : 0;
+        if (ra.xi != nullptr) {                         // parity mode: everything, every update
+            if (ra.llprop_out) ra.llprop_out[orow] = ll_star;
+            if (ra.decisions_out) ra.decisions_out[orow] = acc ? 1 : 0;
+        }
+        batch_outputs(cb, ch, ra, P, c, j, s);
+    } else if (ra.mode == MEMS_MODE_CW) {
+        const double ll_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S : -CUDART_INF;
+        const bool acc = mh_accept(cb.lu[sub][j], ll_star, cb.ll[j]);
+        if (acc) {
+            cb.x[sub][j] = cb.xp[sub][j];
+            cb.ll[j] = ll_star;
+            cb.acc_count[j] += 1u;
+        }
+        if (ra.xi != nullptr) {
+            if (ra.llprop_out) ra.llprop_out[orow] = ll_star;
+            if (ra.decisions_out) ra.decisions_out[orow] = acc ? 1 : 0;
+        }
+        // the window of component `sub` closes before this step's decision is added (same rule as MH)
+        if (adapt_now) {
+            const double lam = adapt_lambda(cb.lambda_cw[sub][j], cb.win_cw[sub][j], ra.adapt_window, cb.adapt_i[j], ra.target_acc);
+            cb.lambda_cw[sub][j] = lam;
+            cb.scale_cw[sub][j] = fmin(lam, 1.0);
+            cb.win_cw[sub][j] = 0;
+            if (sub == P - 1) cb.adapt_i[j] += 1;
+        }
+        cb.win_cw[sub][j] += acc ? 1 : 0;
+        if (sub == P - 1) batch_outputs(cb, ch, ra, P, c, j, s);
+    } else {                                            // delayed acceptance
+        if (sub == 0) {
+            // coarse stage: S covers every da_stride-th time point; rescaled to the full trace length
+            const int Tc = (pb.T + ra.da_stride - 1) / ra.da_stride;
+            const double llc_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S * ((double)pb.T / (double)Tc) : -CUDART_INF;
+            const bool prom = mh_accept(cb.lu[0][j], llc_star, cb.llc[j]);
+            cb.llc_star[j] = llc_star;
+            cb.live[j] = prom ? 1 : 0;
+            if (prom) cb.prom_count[j] += 1u;
+            if (ra.xi != nullptr) {
+                if (ra.llprop_out) ra.llprop_out[orow] = llc_star;
+                if (ra.decisions_out) ra.decisions_out[orow] = prom ? 1 : 0;
+            }
+        } else {
+            bool acc = false;
+            double ll_star = -CUDART_INF;
+            if (cb.live[j]) {
+                ll_star = pb.neg_half_inv_sigma2 * S;
+                // [pi(x*) pi~(x)] / [pi(x) pi~(x*)]
+                acc = mh_accept(cb.lu[1][j], (ll_star - cb.ll[j]) - (cb.llc_star[j] - cb.llc[j]), 0.0);
+            }
+            if (acc) {
+                for (int p = 0; p < P; ++p) cb.x[p][j] = cb.xp[p][j];
+                cb.ll[j] = ll_star;
+                cb.llc[j] = cb.llc_star[j];
+                cb.acc_count[j] += 1u;
+            }
+            if (adapt_now) {
+                const double lam = adapt_lambda(cb.lambda[j], cb.win_acc[j], ra.adapt_window, cb.adapt_i[j], ra.target_acc);
+                cb.lambda[j] = lam;
+                cb.scale[j] = fmin(lam, 1.0);
+                cb.adapt_i[j] += 1;
+                cb.win_acc[j] = 0;
+            }
+            cb.win_acc[j] += acc ? 1 : 0;
+            if (ra.xi != nullptr) {
+                if (ra.llprop_out) ra.llprop_out[orow] = ll_star;
+                if (ra.decisions_out) ra.decisions_out[orow] = acc ? 1 : 0;
+            }
+            batch_outputs(cb, ch, ra, P, c, j, s);
+        }
     }
 }
 
@@ -251,12 +404,12 @@ struct MemsLaunchCtx {
 };
 
 int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
-                      int apply_prior);
+                      int apply_prior, int t_stride);
 int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
 int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
-                    int apply_prior);
+                    int apply_prior, int t_stride);
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
 int mems_tc_choose_nc(int C, int T, int sm_count);
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);
-int mems_draw_launch(const MemsLaunchCtx& ctx, unsigned long long step0, int n_steps, double* xi_out,
-                     double* log_u_out);
+int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned long long step0, int n_steps,
+                     double* xi_out, double* log_u_out);

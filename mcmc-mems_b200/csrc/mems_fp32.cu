@@ -74,20 +74,20 @@ __device__ __forceinline__ float mlp_row(const Fp32Smem& sm, float* a, int P, co
     return out + b7;
 }
 
-// S[j] = sum_t (y_obs[t] - f(xs_j)[t])^2 for the batch; result for chain j lands in Spart[j].
-// y_out (optional) receives the surrogate outputs [chain][T].
+// S[j] = sum over the pass's time points t = 0, stride, 2*stride, ... of (y_obs[t] - f(xs_j)[t])^2;
+// the result for chain j lands in Spart[j].  y_out (optional) receives the surrogate outputs [chain][T].
 __device__ __forceinline__ void eval_batch(Fp32Smem& sm, const double* s_yobs, const float* s_ts, int P, int T,
-                                           float b7, int nc, int ncv, bool skip_dead, float* y_out, int c0) {
+                                           int stride, float b7, int nc, int ncv, bool skip_dead, float* y_out, int c0) {
     const int tid = threadIdx.x;
     const int j = tid & (nc - 1);
     const int tslot = tid / nc;
     const int nts = NT / nc;
     double Sp = 0.0;
-    if (j < ncv && (!skip_dead || sm.cb.inb[j])) {
+    if (j < ncv && (!skip_dead || sm.cb.live[j])) {
         float xs[MEMS_PMAX];
         for (int p = 0; p < P; ++p) xs[p] = sm.cb.xs[p][j];
         float* a = sm.act + tid;
-        for (int t = tslot; t < T; t += nts) {
+        for (int t = tslot * stride; t < T; t += nts * stride) {
             const float out = mlp_row(sm, a, P, xs, s_ts[t], b7);
             if (y_out) y_out[(size_t)(c0 + j) * T + t] = out;
             const double r = s_yobs[t] - (double)out;
@@ -119,22 +119,24 @@ fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs 
         const int c0 = batch * nc;
         const int ncv = min(nc, ch.C - c0);
         __syncthreads();
-        batch_load(sm.cb, ch, P, c0, tid, ncv);
+        batch_load(sm.cb, ch, P, ra.mode, c0, tid, ncv);
         __syncthreads();
         for (int s = 0; s < ra.n_steps; ++s) {
-            if (tid < ncv) batch_propose(sm.cb, sm.c, ch, ra, c0, tid, s);
-            __syncthreads();
-            eval_batch(sm, s_yobs, s_ts, P, T, b7, nc, ncv, true, nullptr, c0);
-            if (tid < ncv) batch_finish(sm.cb, sm.c, ch, ra, c0, tid, s, sm.Spart[tid]);
-            __syncthreads();
+            for (int sub = 0; sub < ra.n_sub; ++sub) {
+                if (tid < ncv) batch_pre(sm.cb, sm.c, ch, ra, c0, tid, s, sub);
+                __syncthreads();
+                eval_batch(sm, s_yobs, s_ts, P, T, batch_pass_stride(ra, sub), b7, nc, ncv, true, nullptr, c0);
+                if (tid < ncv) batch_post(sm.cb, sm.c, ch, ra, c0, tid, s, sub, sm.Spart[tid]);
+                __syncthreads();
+            }
         }
-        batch_store(sm.cb, ch, P, c0, tid, ncv);
+        batch_store(sm.cb, ch, P, ra.mode, c0, tid, ncv);
     }
 }
 
 __global__ void __launch_bounds__(NT, 1)
 fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict__ x, int n, int nc,
-                    float* y_out, double* ll_out, int apply_prior) {
+                    float* y_out, double* ll_out, int apply_prior, int stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Fp32Smem& sm = *reinterpret_cast<Fp32Smem*>(smem_raw);
     const MemsProblem& pb = *pbp;
@@ -156,27 +158,33 @@ fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restric
                 inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
             }
             sm.cb.inb[tid] = inb ? 1 : 0;
+            sm.cb.live[tid] = 1;
         }
         __syncthreads();
-        eval_batch(sm, s_yobs, s_ts, P, T, pb.b7, nc, ncv, false, y_out, c0);
+        eval_batch(sm, s_yobs, s_ts, P, T, stride, pb.b7, nc, ncv, false, y_out, c0);
         if (tid < ncv && ll_out) {
-            const double ll = sm.c.neg_half_inv_sigma2 * sm.Spart[tid];
+            // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
+            const int Tn = (T + stride - 1) / stride;
+            const double ll = sm.c.neg_half_inv_sigma2 * sm.Spart[tid] * ((double)T / (double)Tn);
             ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
         }
     }
 }
 
-__global__ void draw_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, unsigned long long step0,
-                            int n_steps, double* xi_out, double* log_u_out) {
+__global__ void draw_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, int mode, int n_sub,
+                            unsigned long long step0, int n_steps, double* xi_out, double* log_u_out) {
     const MemsConsts& pb = pbp->c;
     const size_t total = (size_t)n_steps * ch.C;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(i / ch.C), c = (int)(i % ch.C);
-        double xi[MEMS_PMAX], lu;
-        draw_update(pb, ch.seed, ch.chain_id0 + (unsigned long long)c, step0 + (unsigned long long)s, xi, lu);
+        double z[4], lu[4], xi[MEMS_PMAX];
+        draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, step0 + (unsigned long long)s, z, lu);
+        if (mode == MEMS_MODE_CW) { for (int p = 0; p < pb.P; ++p) xi[p] = z[p]; }
+        else chol_mul(pb, z, xi);
         if (xi_out)
             for (int p = 0; p < pb.P; ++p) xi_out[((size_t)s * pb.P + p) * ch.C + c] = xi[p];
-        if (log_u_out) log_u_out[i] = lu;
+        if (log_u_out)
+            for (int k = 0; k < n_sub; ++k) log_u_out[((size_t)s * n_sub + k) * ch.C + c] = lu[k];
     }
 }
 
@@ -230,7 +238,7 @@ int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
 }
 
 int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
-                      int apply_prior) {
+                      int apply_prior, int t_stride) {
     const size_t smem = fp32_smem_bytes(ctx.pb_host->c.T);
     cudaError_t e = cudaFuncSetAttribute(fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -240,17 +248,17 @@ int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, floa
     const int nbatch = (n + nc - 1) / nc;
     const int grid = nbatch < 4 * ctx.sm_count ? nbatch : 4 * ctx.sm_count;
     fp32_forward_kernel<<<grid > 0 ? grid : 1, NT, smem, ctx.stream>>>(ctx.pb_dev, x_dev, n, nc, y_out, ll_out,
-                                                                   apply_prior);
+                                                                   apply_prior, t_stride > 0 ? t_stride : 1);
     return (int)cudaGetLastError();
 }
 
-int mems_draw_launch(const MemsLaunchCtx& ctx, unsigned long long step0, int n_steps, double* xi_out,
-                     double* log_u_out) {
+int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned long long step0, int n_steps,
+                     double* xi_out, double* log_u_out) {
     const size_t total = (size_t)n_steps * ctx.chains.C;
     int grid = (int)((total + 255) / 256);
     if (grid > 8 * ctx.sm_count) grid = 8 * ctx.sm_count;
     if (grid < 1) grid = 1;
-    draw_kernel<<<grid, 256, 0, ctx.stream>>>(ctx.pb_dev, ctx.chains, step0, n_steps, xi_out, log_u_out);
+    draw_kernel<<<grid, 256, 0, ctx.stream>>>(ctx.pb_dev, ctx.chains, mode, n_sub, step0, n_steps, xi_out, log_u_out);
     return (int)cudaGetLastError();
 }
 

@@ -61,6 +61,9 @@ struct GroupSmem {
     unsigned long long bar_A[GSLOT];   // workers -> MMA issuer: A operand of the slot is in TMEM
     unsigned long long bar_D[GSLOT];   // tensor core -> workers: accumulator of the slot is complete
     unsigned long long bar_X[GSLOT][4]; // NH=2: upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
+    unsigned long long bar_S;          // workers -> MMA issuer: ctrl_tiles of the next pass is valid
+    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
+    int pad_;
 };
 
 struct TcSmem {
@@ -295,22 +298,30 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// MMA issuer of one group: serves the group's two slots in the fixed order the workers produce them.
-__device__ __forceinline__ void mma_serve_eval(TcSmem& sm, GroupSmem& gs, int g, int n_tiles, uint32_t& phA) {
+// MMA issuer of one group: for every surrogate pass the workers announce (ctrl_tiles via bar_S) it serves
+// the group's two slots in the fixed order the workers produce them; ctrl_tiles < 0 ends the loop.
+__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = sm.tmem_base + (uint32_t)(g * GSLOT * 128);
-    const int n_pairs = (n_tiles + 1) >> 1;
-    for (int pair = 0; pair < n_pairs; ++pair) {
+    uint32_t phA = 0, phS = 0;
+    for (;;) {
+        mbar_wait(&gs.bar_S, phS);
+        phS ^= 1u;
+        const int n_tiles = *reinterpret_cast<volatile int*>(&gs.ctrl_tiles);
+        if (n_tiles < 0) break;
+        const int n_pairs = (n_tiles + 1) >> 1;
+        for (int pair = 0; pair < n_pairs; ++pair) {
 #pragma unroll 1
-        for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+            for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
-            for (int s = 0; s < GSLOT; ++s) {
-                if (pair * 2 + s < n_tiles) {
-                    mbar_wait(&gs.bar_A[s], (phA >> s) & 1u);
-                    phA ^= (1u << s);
-                    tc_fence_after();
-                    issue_layer(wimg, base + s * 128, layer);
-                    umma_commit(&gs.bar_D[s]);
+                for (int s = 0; s < GSLOT; ++s) {
+                    if (pair * 2 + s < n_tiles) {
+                        mbar_wait(&gs.bar_A[s], (phA >> s) & 1u);
+                        phA ^= (1u << s);
+                        tc_fence_after();
+                        issue_layer(wimg, base + s * 128, layer);
+                        umma_commit(&gs.bar_D[s]);
+                    }
                 }
             }
         }
@@ -346,12 +357,23 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
 template <int NH>
 __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, gthreads(NH)); }
 
+// group barrier + OR-reduction of a predicate over the group's worker threads
+template <int NH>
+__device__ __forceinline__ bool group_any(int g, bool pred) {
+    uint32_t out;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+        "barrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(out) : "r"((uint32_t)pred), "r"(1 + g), "r"(gthreads(NH)) : "memory");
+    return out != 0;
+}
+
 // The worker threads of group g evaluate one batch.  Thread (row, h) owns TMEM lane `row` of both slots and
 // columns [64/NH * h, 64/NH * (h+1)) of it; row `row` of every tile is (chain j = row mod nc, time sub-row row / nc).
 template <int P, int NH>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
-                                              const float* s_ts, int T, int nc, int log2nc, int ncv, bool skip_dead,
-                                              float* y_out, int c0, uint32_t& phD) {
+                                              const float* s_ts, int T, int stride, int nc, int log2nc, int ncv,
+                                              bool skip_dead, float* y_out, int c0, uint32_t& phD) {
     constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
     const int gt = threadIdx.x & (gthreads(NH) - 1);
     const int row = gt & 127;
@@ -360,10 +382,15 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const int j = row & (nc - 1);
     const int sub = row >> log2nc;
     const int tpt = 128 >> log2nc;                    // time points per tile
-    const int n_tiles = (T + tpt - 1) / tpt;
+    const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
+    const int n_tiles = (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
-    const bool chain_live = (j < ncv) && (!skip_dead || gs.cb.inb[j]);
+    const bool chain_live = (j < ncv) && (!skip_dead || gs.cb.live[j]);
+    if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
+        *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
+        mbar_arrive(&gs.bar_S);
+    }
 
     uint32_t a1[16];
     if (h == 0) {
@@ -381,8 +408,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     for (int s = 0; s < GSLOT; ++s) {
         if (s < n_tiles) {
             if (h == 0) {
-                const int t = s * tpt + sub;
-                put_input<P>(a1, P, s_ts[t < T ? t : T - 1]);
+                const int ti = s * tpt + sub;
+                put_input<P>(a1, P, s_ts[ti < Tn ? ti * stride : 0]);
                 tmem_st16(tD0 + s * 128 + 64, a1);
                 tc_wait_st();
             }
@@ -437,8 +464,9 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         }
                         if (h == 0) {
                             o += sm.b7;
-                            const int t = tile * tpt + sub;
-                            if (chain_live && t < T) {
+                            const int ti = tile * tpt + sub;
+                            const int t = ti * stride;
+                            if (chain_live && ti < Tn) {
                                 if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
                                 const double r = s_yobs[t] - (double)o;
                                 Sp = fma(r, r, Sp);
@@ -448,8 +476,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         const int nt = tile + GSLOT;
                         if (nt < n_tiles) {
                             if (h == 0) {
-                                const int t2 = nt * tpt + sub;
-                                put_input<P>(a1, P, s_ts[t2 < T ? t2 : T - 1]);
+                                const int ti2 = nt * tpt + sub;
+                                put_input<P>(a1, P, s_ts[ti2 < Tn ? ti2 * stride : 0]);
                                 tmem_st16(tD + 64, a1);
                                 tc_wait_st();
                             }
@@ -486,6 +514,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
                 mbar_init(&sm.grp[g].bar_D[s], 1);
                 for (int q = 0; q < 4; ++q) mbar_init(&sm.grp[g].bar_X[s][q], 32);
             }
+        for (int g = 0; g < NGROUP; ++g) { mbar_init(&sm.grp[g].bar_S, 1); sm.grp[g].ctrl_tiles = 0; }
         mbar_init(&sm.bar_w, 1);
         sm.c = pb.c;
         fence_barrier_init();
@@ -540,11 +569,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NW) {
-        if ((tid & 31) == 0) {
-            uint32_t phA = 0;
-            for (int batch = gid; batch < nbatch; batch += gstride)
-                for (int s = 0; s < ra.n_steps; ++s) mma_serve_eval(sm, gs, g, n_tiles, phA);
-        }
+        if ((tid & 31) == 0) mma_issuer_loop(sm, gs, g);
         __syncwarp();
     } else {
         const int gt = tid & (GT - 1);
@@ -553,14 +578,25 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
             const int c0 = batch * nc;
             const int ncv = min(nc, ch.C - c0);
             group_bar_sync<NH>(g);
-            batch_load(gs.cb, ch, P, c0, gt, ncv);
+            batch_load(gs.cb, ch, P, ra.mode, c0, gt, ncv);
             for (int s = 0; s < ra.n_steps; ++s) {
-                if (gt < ncv) batch_propose(gs.cb, sm.c, ch, ra, c0, gt, s);
-                group_bar_sync<NH>(g);
-                tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, true, nullptr, c0, phD);
-                if (gt < ncv) batch_finish(gs.cb, sm.c, ch, ra, c0, gt, s, gs.Spart[gt]);
+                for (int sub = 0; sub < ra.n_sub; ++sub) {
+                    if (gt < ncv) batch_pre(gs.cb, sm.c, ch, ra, c0, gt, s, sub);
+                    // barrier + "does any chain of the batch need this pass?" (all proposals outside the prior box,
+                    // or no proposal promoted by the DA first stage -> the pass is skipped entirely)
+                    const bool any = group_any<NH>(g, gt < ncv && gs.cb.live[gt]);
+                    if (any)
+                        tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, log2nc, ncv, true,
+                                             nullptr, c0, phD);
+                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, any ? gs.Spart[gt] : 0.0);
+                }
             }
-            batch_store(gs.cb, ch, P, c0, gt, ncv);
+            batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
+        }
+        group_bar_sync<NH>(g);
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
         }
     }
     tc_epilogue_free<NH>(sm);
@@ -569,7 +605,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
 template <int P, int NH>
 __global__ void __launch_bounds__(nthreads(NH), 1)
 tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict__ x, int n, int nc, float* y_out,
-                  double* ll_out, int apply_prior) {
+                  double* ll_out, int apply_prior, int stride) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     const MemsProblem& pb = *pbp;
@@ -588,10 +624,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NW) {
-        if ((tid & 31) == 0) {
-            uint32_t phA = 0;
-            for (int batch = gid; batch < nbatch; batch += gstride) mma_serve_eval(sm, gs, g, n_tiles, phA);
-        }
+        if ((tid & 31) == 0) mma_issuer_loop(sm, gs, g);
         __syncwarp();
     } else {
         const int gt = tid & (GT - 1);
@@ -608,13 +641,21 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
                     inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
                 }
                 gs.cb.inb[gt] = inb ? 1 : 0;
+                gs.cb.live[gt] = 1;
             }
             group_bar_sync<NH>(g);
-            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, nc, log2nc, ncv, false, y_out, c0, phD);
+            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, stride, nc, log2nc, ncv, false, y_out, c0, phD);
             if (gt < ncv && ll_out) {
-                const double ll = sm.c.neg_half_inv_sigma2 * gs.Spart[gt];
+                // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
+                const int Tn = (T + stride - 1) / stride;
+                const double ll = sm.c.neg_half_inv_sigma2 * gs.Spart[gt] * ((double)T / (double)Tn);
                 ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
             }
+        }
+        group_bar_sync<NH>(g);
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
         }
     }
     tc_epilogue_free<NH>(sm);
@@ -851,7 +892,8 @@ int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
 }
 
 int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float* y_out, double* ll_out,
-                    int apply_prior) {
+                    int apply_prior, int t_stride) {
+    if (t_stride < 1) t_stride = 1;
     const size_t smem = tc_smem_bytes(ctx.pb_host->c.T);
     const int nc = mems_tc_choose_nc(n, ctx.pb_host->c.T, ctx.sm_count);
     const int nbatch = (n + nc - 1) / nc;
@@ -860,9 +902,9 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
     const int gr = grid > 0 ? grid : 1;
     if (tc_nh() == 1)
         return launch_by_p<1>(ctx.pb_host->c.P, tc_forward_kernel<1, 1>, tc_forward_kernel<2, 1>, tc_forward_kernel<3, 1>,
-                              tc_forward_kernel<4, 1>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior);
+                              tc_forward_kernel<4, 1>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
     return launch_by_p<2>(ctx.pb_host->c.P, tc_forward_kernel<1, 2>, tc_forward_kernel<2, 2>, tc_forward_kernel<3, 2>,
-                          tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior);
+                          tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
 }
 
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st) {

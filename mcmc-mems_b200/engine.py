@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MemsError, PATH_FP32, PATH_TC  # noqa: F401
+from ._lib import MemsError, PATH_FP32, PATH_TC, SAMPLER_MH, SAMPLER_CWMH, SAMPLER_DA  # noqa: F401
 
 
 def _require_cuda(device: int = 0):
@@ -88,6 +88,8 @@ class MHEngine:
         h = C.c_void_p()
         _lib.check(self._L.mems_create(C.byref(cfg), C.byref(h)), "mems_create")
         self._h = h
+        self.sampler = SAMPLER_MH
+        self.n_sub = 1
         try:
             Ws = [_host(k, np.float32) for k, _, _ in spec.layers]
             bs = [_host(b, np.float32) for _, b, _ in spec.layers]
@@ -169,6 +171,18 @@ class MHEngine:
         _lib.check(self._L.mems_forward(self._h, _ptr(xt), n, _ptr(y), _ptr(ll), _stream(self.device)), "mems_forward")
         return y, ll
 
+    # -- sampler variant ---------------------------------------------------------
+    def set_sampler(self, sampler: int, cw_scale=None, da_stride: int = 4):
+        """SAMPLER_MH (reference), SAMPLER_CWMH (component-wise; ``cw_scale[P]`` = initial per-component
+        proposal std) or SAMPLER_DA (delayed acceptance; coarse stage = every ``da_stride``-th time point).
+        Call before :meth:`init_chains`."""
+        cw = None if cw_scale is None else _host(np.broadcast_to(np.asarray(cw_scale, np.float64), (self.P,)))
+        _lib.check(self._L.mems_set_sampler(self._h, int(sampler), None if cw is None else cw.ctypes.data,
+                                            int(da_stride)), "mems_set_sampler")
+        self.sampler = int(sampler)
+        self.n_sub = self.P if sampler == SAMPLER_CWMH else (2 if sampler == SAMPLER_DA else 1)
+        self.da_stride = int(da_stride)
+
     # -- chains ------------------------------------------------------------------
     def init_chains(self, x0, scale0: float = 0.1, seed: int = 0, chain_id0: int = 0):
         xd = self._dev(x0).reshape(self.C, self.P)
@@ -192,21 +206,23 @@ class MHEngine:
                                     _ptr(loglik), _stream(self.device)), "mems_run")
 
     def run_explicit(self, xi, log_u, adapt_window: int = 0):
-        """xi: [n_steps, P, C], log_u: [n_steps, C].  Returns (samples, loglik_prop, decisions)."""
+        """xi: [n_steps, P, C]; log_u: [n_steps, C] (MH) or [n_steps, n_sub, C] (CWMH: n_sub = P, DA: 2).
+        Returns (samples [n_steps,P,C], loglik_prop, decisions) with the shape of log_u."""
         xid, lud = self._dev(xi), self._dev(log_u)
         n_steps = xid.shape[0]
-        if xid.shape != (n_steps, self.P, self.C) or lud.shape != (n_steps, self.C):
-            raise ValueError("xi must be [n_steps,P,C] and log_u [n_steps,C]")
+        lshape = (n_steps, self.C) if (self.n_sub == 1 and lud.ndim == 2) else (n_steps, self.n_sub, self.C)
+        if xid.shape != (n_steps, self.P, self.C) or tuple(lud.shape) != lshape:
+            raise ValueError(f"xi must be [n_steps,P,C] and log_u {list(lshape)}")
         smp = self._new(n_steps, self.P, self.C)
-        llp = self._new(n_steps, self.C)
-        dec = self._new(n_steps, self.C, dtype=torch.uint8)
+        llp = self._new(*lshape)
+        dec = self._new(*lshape, dtype=torch.uint8)
         _lib.check(self._L.mems_run_explicit(self._h, n_steps, int(adapt_window), _ptr(xid), _ptr(lud),
                                              _ptr(smp), _ptr(llp), _ptr(dec), _stream(self.device)), "mems_run_explicit")
         return smp, llp, dec
 
     def draw(self, step0: int, n_steps: int):
         xi = self._new(n_steps, self.P, self.C)
-        lu = self._new(n_steps, self.C)
+        lu = self._new(n_steps, self.C) if self.n_sub == 1 else self._new(n_steps, self.n_sub, self.C)
         _lib.check(self._L.mems_draw(self._h, C.c_uint64(step0), int(n_steps), _ptr(xi), _ptr(lu),
                                      _stream(self.device)), "mems_draw")
         return xi, lu
@@ -220,6 +236,14 @@ class MHEngine:
         _lib.check(self._L.mems_get_state(self._h, _ptr(x), _ptr(ll), _ptr(sc), _ptr(ac), C.byref(steps),
                                           _stream(self.device)), "mems_get_state")
         return {"x": x, "loglik": ll, "scale": sc, "accept_count": ac, "steps_done": int(steps.value)}
+
+    def aux_state(self):
+        """Variant-specific state: per-component scales (CWMH), coarse log-likelihood and promotions (DA)."""
+        sc = self._new(self.P, self.C)
+        llc = self._new(self.C)
+        pc = self._new(self.C, dtype=torch.int32)
+        _lib.check(self._L.mems_get_aux(self._h, _ptr(sc), _ptr(llc), _ptr(pc), _stream(self.device)), "mems_get_aux")
+        return {"scale_cw": sc, "loglik_coarse": llc, "promote_count": pc}
 
     @property
     def launches(self) -> int:

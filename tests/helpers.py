@@ -101,3 +101,87 @@ def check_explicit_run(pb, x0, scale, xi, log_u, smp, llp, dec, band, ll0=None):
                 ll_cur[c] = ll_star[c]
         state_err = max(state_err, float(np.max(np.abs(smp[s].T - prev))))
     return {"flips": flips, "near_ties": near, "max_ll_err": max_err, "state_err": state_err}
+
+
+def _ll_of(pb, X, stride=1):
+    """Oracle log-likelihood core of points X [n,P] on time points 0, stride, 2*stride, ... (rescaled by T/Tc),
+    with -inf outside the prior box."""
+    from oracle import batched_forward
+    f = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], X)
+    T = f.shape[1]
+    idx = np.arange(0, T, stride)
+    r = pb["y_obs"][None, idx] - f[:, idx].astype(np.float64)
+    ll = -0.5 * np.sum(r * r, axis=1) / pb["sigma2"] * (T / len(idx))
+    inb = np.all((X >= pb["low"]) & (X <= pb["high"]), axis=1)
+    return np.where(inb, ll, -np.inf)
+
+
+def _tally(res, want, got, margin, band):
+    if want != got:
+        if margin <= band:
+            res["near_ties"] += 1
+        else:
+            res["flips"] += 1
+
+
+def check_explicit_cwmh(pb, x0, cw_scale, z, log_u, smp, llp, dec, band):
+    """Component-wise MH replay (cuqi CWMH.single_update semantics).  z, log_u: [S,C,P];
+    kernel outputs smp [S,P,C], llp/dec [S,P,C]."""
+    from oracle import decide
+    S, C, P = z.shape
+    cur = np.asarray(x0, np.float64).copy()
+    ll_cur = _ll_of(pb, cur)
+    res = {"flips": 0, "near_ties": 0, "max_ll_err": 0.0, "state_err": 0.0}
+    for s in range(S):
+        x_o = cur + np.asarray(cw_scale)[None, :] * z[s]
+        for p in range(P):
+            prop = cur.copy()
+            prop[:, p] = x_o[:, p]
+            ll_star = _ll_of(pb, prop)
+            k = llp[s, p]
+            fin = np.isfinite(ll_star)
+            assert np.array_equal(np.isfinite(k), fin)
+            if fin.any():
+                res["max_ll_err"] = max(res["max_ll_err"], float(np.max(np.abs(k[fin] - ll_star[fin]) / np.maximum(1.0, np.abs(ll_star[fin])))))
+            for c in range(C):
+                want, got = decide(log_u[s, c, p], ll_star[c], ll_cur[c]), bool(dec[s, p, c])
+                _tally(res, want, got, abs(log_u[s, c, p] - min(0.0, ll_star[c] - ll_cur[c])), band)
+                if got:
+                    cur[c, p] = prop[c, p]
+                    ll_cur[c] = ll_star[c]
+        res["state_err"] = max(res["state_err"], float(np.max(np.abs(smp[s].T - cur))))
+    return res
+
+
+def check_explicit_da(pb, x0, scale, stride, xi, log_u, smp, llp, dec, band):
+    """Delayed-acceptance replay (Christen & Fox).  xi [S,C,P], log_u [S,C,2]; kernel llp/dec [S,2,C]."""
+    from oracle import decide
+    S, C, P = xi.shape
+    cur = np.asarray(x0, np.float64).copy()
+    lf, lc = _ll_of(pb, cur), _ll_of(pb, cur, stride)
+    res = {"flips": 0, "near_ties": 0, "max_ll_err": 0.0, "state_err": 0.0, "promoted": 0, "accepted": 0}
+    for s in range(S):
+        prop = cur + scale * xi[s]
+        lc_star, lf_star = _ll_of(pb, prop, stride), _ll_of(pb, prop)
+        fin = np.isfinite(lc_star)
+        assert np.array_equal(np.isfinite(llp[s, 0]), fin)
+        if fin.any():
+            res["max_ll_err"] = max(res["max_ll_err"], float(np.max(np.abs(llp[s, 0][fin] - lc_star[fin]) / np.maximum(1.0, np.abs(lc_star[fin])))))
+        for c in range(C):
+            want1, got1 = decide(log_u[s, c, 0], lc_star[c], lc[c]), bool(dec[s, 0, c])
+            _tally(res, want1, got1, abs(log_u[s, c, 0] - min(0.0, lc_star[c] - lc[c])), band)
+            got2 = bool(dec[s, 1, c])
+            if got1:
+                res["promoted"] += 1
+                ratio = (lf_star[c] - lf[c]) - (lc_star[c] - lc[c])
+                want2 = decide(log_u[s, c, 1], ratio, 0.0)
+                _tally(res, want2, got2, abs(log_u[s, c, 1] - min(0.0, ratio)), band)
+                assert abs(llp[s, 1, c] - lf_star[c]) <= 1e-3 * max(1.0, abs(lf_star[c]))
+            else:
+                assert not got2 and np.isneginf(llp[s, 1, c])
+            if got2:
+                res["accepted"] += 1
+                cur[c] = prop[c]
+                lf[c], lc[c] = lf_star[c], lc_star[c]
+        res["state_err"] = max(res["state_err"], float(np.max(np.abs(smp[s].T - cur))))
+    return res

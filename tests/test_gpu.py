@@ -372,3 +372,72 @@ def test_reference_shaped_api_end_to_end():
     assert b.samples.shape == (3, 300) and np.all(b.compute_ess() > 10)
     many = MH(target=post, proposal=prop, x0=np.tile(x_opt, (16, 1)), seed=2).sample_adapt(1500, 100)
     assert many.samples.shape == (16, 3, 1500) and np.all(many.compute_rhat() < 1.2)
+
+
+# ----------------------------------------------------------------------------- sampler variants (unpinned in the reference)
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_componentwise_mh_matches_oracle_semantics(path):
+    """CWMH (cuqi.sampler.CWMH semantics): P surrogate passes per update."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("geometric")
+    C, S, P = 40, 10, 3
+    rng = np.random.default_rng(8)
+    cw = 0.5 * np.sqrt(pb["sigma2"] * np.diag(pb["cov"]))
+    x0 = pb["x_opts"][0][None, :] + 0.3 * rng.standard_normal((C, P)) * cw
+    z = rng.standard_normal((S, C, P))
+    log_u = np.log(rng.random((S, C, P)))
+    eng = helpers.engine(pb, C, path)
+    eng.set_sampler(E.SAMPLER_CWMH, cw_scale=cw)
+    eng.init_chains(x0, scale0=0.1)
+    smp, llp, dec = eng.run_explicit(z.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
+    res = helpers.check_explicit_cwmh(pb, x0, cw, z, log_u, smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy(), BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert 0.1 < dec.float().mean().item() < 0.9
+    assert eng.state()["accept_count"].sum().item() == int(dec.sum().item())
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_delayed_acceptance_matches_oracle_semantics(path):
+    """DA (Christen & Fox 2005): coarse stage = every 5th time point."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("geometric")
+    C, S, P, stride = 48, 12, 3, 5
+    x0, xi, _ = _explicit_inputs(pb, C, S, 9)
+    log_u = np.log(np.random.default_rng(10).random((S, C, 2)))
+    eng = helpers.engine(pb, C, path)
+    eng.set_sampler(E.SAMPLER_DA, da_stride=stride)
+    eng.init_chains(x0, scale0=0.15)
+    aux = eng.aux_state()
+    assert np.allclose(aux["loglik_coarse"].cpu().numpy(), helpers._ll_of(pb, x0, stride), rtol=1e-3)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
+    res = helpers.check_explicit_da(pb, x0, 0.15, stride, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy(), BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert 0 < res["accepted"] <= res["promoted"] < C * S
+    assert eng.aux_state()["promote_count"].sum().item() == res["promoted"]
+    eng.close()
+
+
+def test_variants_sample_the_same_posterior():
+    """Invariance: CWMH and DA chains target the same posterior as random-walk MH (within MC error)."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("geometric")
+    C, N = 512, 3000
+    sd = np.sqrt(pb["sigma2"] * np.diag(pb["cov"]))
+    x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
+    out = {}
+    for name, sampler, kw, scale0 in (("mh", E.SAMPLER_MH, {}, 0.128), ("cw", E.SAMPLER_CWMH, {"cw_scale": 1.2 * sd}, 0.1),
+                                      ("da", E.SAMPLER_DA, {"da_stride": 3}, 0.128)):
+        eng = helpers.engine(pb, C, 1)
+        eng.set_sampler(sampler, **kw)
+        eng.init_chains(x0, scale0=scale0, seed=77)
+        eng.run(1000, 0, 1, keep_samples=False)
+        smp, _ = eng.run(N, 0, 10)
+        S = smp.cpu().numpy().transpose(1, 0, 2).reshape(3, -1)
+        out[name] = (S.mean(axis=1), S.std(axis=1), eng.state()["accept_count"].double().mean().item() / (N + 1000))
+        eng.close()
+    # single-component moves mix slowly along the strongly correlated posterior ridge: wider MC tolerance for CWMH
+    for k, tol_m, tol_s in (("cw", 0.35, 0.25), ("da", 0.1, 0.1)):
+        assert np.all(np.abs(out[k][0] - out["mh"][0]) < tol_m * out["mh"][1]), (k, out)
+        assert np.all(np.abs(out[k][1] / out["mh"][1] - 1) < tol_s), (k, out)
+    assert out["da"][2] <= out["mh"][2] + 0.01      # DA can only lower the acceptance rate
