@@ -156,6 +156,14 @@ int  mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths,
                       const float* const* W, const float* const* b, const float* X_dev,
                       int64_t n, float* Y_dev, void* stream);
 
+/* Split-chain moments of kept samples: the sufficient statistics of split-R-hat, computed where the
+ * samples live.  Replaces the first step of Samples.compute_rhat (arviz underneath; call site
+ * tests/Xaccelerometer_geometric/identification.ipynb:311) at scale.
+ * samples_dev [n_keep][P][C] f64 -> out_dev [4][P][C] f64: mean and unbiased variance of the first
+ * n_keep/2 draws, then of the last n_keep/2 draws, per (parameter, chain). */
+int  mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params,
+                        int32_t n_chains, double* out_dev, void* stream);
+
 /* Hardware self-test of the tensor-core plumbing the MH kernels rely on (UMMA descriptors,
  * 128B swizzle, TMEM operand packing, tcgen05.ld/st, commit->mbarrier):
  * D[128][64] (f32) = A[128][64] (f16) * B[64][64]^T (f16), all device pointers, row-major.

@@ -9,13 +9,13 @@ from .model import NN_Model  # noqa: F401
 from .preprocessing import preprocessing, FixtureProcessor  # noqa: F401
 from .utils import (create_forward_model_function, least_squares_optimization,  # noqa: F401
                     objective_function, surrogate_spec)
-from .cuqi_compat import (Gaussian, Uniform, JointDistribution, Posterior, Model, MH, Samples,  # noqa: F401
-                          BatchedSamples, Continuous1D, Discrete)
-from . import diagnostics, h5lite  # noqa: F401
+from .cuqi_compat import (Gaussian, Uniform, JointDistribution, Posterior, Model, MH, CWMH,  # noqa: F401
+                          DelayedAcceptanceMH, Samples, BatchedSamples, Continuous1D, Discrete)
+from . import diagnostics, distributed, h5lite  # noqa: F401
 
 __all__ = [
     "MHEngine", "SurrogateSpec", "NN_Model", "preprocessing", "FixtureProcessor",
     "create_forward_model_function", "least_squares_optimization", "Gaussian", "Uniform",
-    "JointDistribution", "Posterior", "Model", "MH", "Samples", "BatchedSamples", "Continuous1D",
+    "JointDistribution", "Posterior", "Model", "MH", "CWMH", "DelayedAcceptanceMH", "Samples", "BatchedSamples", "Continuous1D",
     "Discrete", "diagnostics", "h5lite", "mlp_forward", "MemsError", "PATH_FP32", "PATH_TC",
 ]

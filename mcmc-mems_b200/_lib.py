@@ -24,7 +24,7 @@ SAMPLER_DA = 2
 EXPORTS = [
     "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
     "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
-    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_launch_count", "mems_selftest_umma",
+    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_selftest_umma",
 ]
 
 
@@ -69,6 +69,7 @@ def lib():
     L.mems_get_aux.argtypes = [vp, vp, vp, vp, vp]
     L.mems_set_sampler.argtypes = [vp, i32, vp, i32]
     L.mems_mlp_forward.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(vp), C.POINTER(vp), vp, i64, vp, vp]
+    L.mems_chain_moments.argtypes = [i32, vp, i32, i32, i32, vp, vp]
     L.mems_launch_count.argtypes = [vp]
     L.mems_launch_count.restype = i64
     L.mems_selftest_umma.argtypes = [i32, i32, vp, vp, vp, vp]

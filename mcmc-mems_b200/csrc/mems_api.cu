@@ -12,6 +12,7 @@
 
 int mems_mlp_forward_launch(int n_layers, const int* widths, const float* const* Wd, const float* const* bd,
                             const float* X, long long n, float* Y, int sm_count, cudaStream_t st);
+int mems_chain_moments_launch(const double* samples, int n_keep, int P, int C, double* out, int sm_count, cudaStream_t st);
 size_t mems_tc_wimg_bytes();
 void mems_tc_build_wimg(const MemsProblem& pb, void* host_img);
 
@@ -420,6 +421,22 @@ int mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths, co
     cudaStreamSynchronize(st);   // weights are temporaries of this call
     for (int l = 0; l < n_layers; ++l) { cudaFree(Wd[l]); cudaFree(bd[l]); }
     return rc;
+}
+
+int mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params, int32_t n_chains,
+                       double* out_dev, void* stream) {
+    if (!samples_dev || !out_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (n_keep < 4 || n_params < 1 || n_chains < 1) return fail(MEMS_E_INVALID, "need n_keep >= 4, n_params >= 1, n_chains >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int e = mems_chain_moments_launch(samples_dev, n_keep, n_params, n_chains, out_dev, prop.multiProcessorCount,
+                                            reinterpret_cast<cudaStream_t>(stream));
+    if (e != 0) return fail(MEMS_E_CUDA, "chain_moments launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
 }
 
 int64_t mems_launch_count(mems_handle_t h) { return h ? h->launches : 0; }

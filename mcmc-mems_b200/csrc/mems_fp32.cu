@@ -223,6 +223,28 @@ mlp_forward_kernel(MlpDesc d, const float* __restrict__ X, long long n, float* _
     }
 }
 
+// Per-chain split-chain moments of the kept samples (the sufficient statistics of split-R-hat):
+// out[0] = mean of the first half, out[1] = unbiased variance of the first half, out[2], out[3] = same for
+// the last half; each [P][C].  One thread per (parameter, chain), Welford updates, chain-minor reads coalesce.
+__global__ void chain_moments_kernel(const double* __restrict__ samples, int n_keep, int P, int C, double* __restrict__ out) {
+    const size_t total = (size_t)P * C;
+    const int half = n_keep / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        for (int hsel = 0; hsel < 2; ++hsel) {
+            const int k0 = hsel == 0 ? 0 : n_keep - half;
+            double mean = 0.0, m2 = 0.0;
+            for (int k = 0; k < half; ++k) {
+                const double v = samples[(size_t)(k0 + k) * total + i];
+                const double d = v - mean;
+                mean += d / (double)(k + 1);
+                m2 = fma(d, v - mean, m2);
+            }
+            out[(size_t)(2 * hsel) * total + i] = mean;
+            out[(size_t)(2 * hsel + 1) * total + i] = half > 1 ? m2 / (double)(half - 1) : 0.0;
+        }
+    }
+}
+
 size_t fp32_smem_bytes(int T) { return sizeof(Fp32Smem) + (size_t)T * (sizeof(double) + sizeof(float)) + 16; }
 
 }  // namespace
@@ -259,6 +281,15 @@ int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned lon
     if (grid > 8 * ctx.sm_count) grid = 8 * ctx.sm_count;
     if (grid < 1) grid = 1;
     draw_kernel<<<grid, 256, 0, ctx.stream>>>(ctx.pb_dev, ctx.chains, mode, n_sub, step0, n_steps, xi_out, log_u_out);
+    return (int)cudaGetLastError();
+}
+
+int mems_chain_moments_launch(const double* samples, int n_keep, int P, int C, double* out, int sm_count, cudaStream_t st) {
+    const size_t total = (size_t)P * C;
+    long long blocks = (long long)((total + 255) / 256);
+    if (blocks > 16LL * sm_count) blocks = 16LL * sm_count;
+    if (blocks < 1) blocks = 1;
+    chain_moments_kernel<<<(int)blocks, 256, 0, st>>>(samples, n_keep, P, C, out);
     return (int)cudaGetLastError();
 }
 

@@ -93,15 +93,6 @@ __device__ __forceinline__ void mbar_arrive(void* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -562,8 +553,6 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     const int T = sm.c.T, nc = ra.nc, log2nc = ilog2(ra.nc);
     const int tid = threadIdx.x;
     const int nbatch = (ch.C + nc - 1) / nc;
-    const int tpt = 128 >> log2nc;
-    const int n_tiles = (T + tpt - 1) / tpt;
     const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
@@ -617,8 +606,6 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const int T = sm.c.T, log2nc = ilog2(nc);
     const int tid = threadIdx.x;
     const int nbatch = (n + nc - 1) / nc;
-    const int tpt = 128 >> log2nc;
-    const int n_tiles = (T + tpt - 1) / tpt;
     const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;

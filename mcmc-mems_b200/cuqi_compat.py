@@ -20,7 +20,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import diagnostics
-from .engine import MHEngine, SurrogateSpec, PATH_FP32, PATH_TC  # noqa: F401
+from .engine import (MHEngine, SurrogateSpec, PATH_FP32, PATH_TC, SAMPLER_MH, SAMPLER_CWMH,  # noqa: F401
+                     SAMPLER_DA)
 
 
 # -- geometries ----------------------------------------------------------------------------
@@ -280,10 +281,21 @@ class MH:
             raise TypeError("the model's forward function must come from create_forward_model_function")
         self.spec: SurrogateSpec = fwd.spec
 
+    #: sampler variant run by the engine; subclasses override
+    _sampler = SAMPLER_MH
+
     def _engine(self, C) -> MHEngine:
         cov = self.proposal._dense_cov(self.dim)
-        return MHEngine(self.spec, self.target.data, self.target.sigma2, self.target.prior.low,
-                        self.target.prior.high, cov, n_chains=C, path=self.path, device=self.device)
+        eng = MHEngine(self.spec, self.target.data, self.target.sigma2, self.target.prior.low,
+                       self.target.prior.high, cov, n_chains=C, path=self.path, device=self.device)
+        self._configure(eng)
+        return eng
+
+    def _configure(self, eng: MHEngine):
+        pass
+
+    def _adapt_window(self, N):
+        return int(0.1 * N)
 
     def sample(self, N, Nb=0):
         if self.scale is None:
@@ -303,7 +315,7 @@ class MH:
         eng = self._engine(C)
         try:
             eng.init_chains(x0, scale0=float(self.scale), seed=self.seed, chain_id0=self.chain_id0)
-            Na = int(0.1 * N) if adapt else 0
+            Na = self._adapt_window(N) if adapt else 0
             Ns = N + Nb
             const = eng.loglik_const + eng.logprior_const
             st0 = eng.state()
@@ -316,7 +328,8 @@ class MH:
             else:
                 smp, ll = eng.run(Ns - 1, Na, 1, keep_samples=True, keep_loglik=True)
                 pre = [(st0["x"].cpu().numpy(), st0["loglik"].cpu().numpy())]
-                acc_kept = eng.state()["accept_count"].cpu().numpy().astype(np.int64) + 1   # acc[0] = 1
+                per = self.dim if self._sampler == SAMPLER_CWMH else 1                       # CWMH counts per component
+                acc_kept = eng.state()["accept_count"].cpu().numpy().astype(np.int64) + per   # acc[0] = 1
             st = eng.state()
             S = np.empty((C, self.dim, N))
             LL = np.empty((C, N))
@@ -329,7 +342,7 @@ class MH:
                 S[:, :, k:] = smp.cpu().numpy().transpose(2, 1, 0)
                 LL[:, k:] = ll.cpu().numpy().T
             LL = LL + const
-            acc_rate = acc_kept / float(N)
+            acc_rate = acc_kept / float(N * (self.dim if self._sampler == SAMPLER_CWMH else 1))
             scale = st["scale"].cpu().numpy()
             self.scale = float(scale[0]) if C == 1 else scale
         finally:
@@ -338,3 +351,37 @@ class MH:
             print("\nAverage acceptance rate:", acc_rate[0], "MCMC scale:", scale[0], "\n")
             return Samples(S[0], LL[0], float(acc_rate[0]), float(scale[0]), self.target.model.domain_geometry)
         return BatchedSamples(S, LL, acc_rate, scale)
+
+
+class DelayedAcceptanceMH(MH):
+    """Two-stage (Christen & Fox 2005) variant of :class:`MH`: the first stage scores every
+    ``stride``-th time point of the trace.  Not part of CUQIpy 0.8.0 nor of the reference
+    (SURVEY.md F2); same constructor and return types as :class:`MH`."""
+    _sampler = SAMPLER_DA
+
+    def __init__(self, *a, stride: int = 4, **k):
+        super().__init__(*a, **k)
+        self.stride = int(stride)
+
+    def _configure(self, eng):
+        eng.set_sampler(SAMPLER_DA, da_stride=self.stride)
+
+
+class CWMH(MH):
+    """``cuqi.sampler.CWMH`` look-alike (component-wise MH; never used by the reference).
+    ``scale`` is the per-component proposal std (scalar or length-dim vector); the proposal is
+    CUQIpy's default ``Normal(location, scale)``; adaptation uses ``Na = int(0.012*N)`` and the target
+    ``0.21/dim + 0.23``."""
+    _sampler = SAMPLER_CWMH
+
+    def __init__(self, target, proposal=None, scale=1, x0=None, dim=None, **k):
+        if proposal is not None:
+            raise ValueError("CWMH on the GPU supports CUQIpy's default Normal(location, scale) proposal only")
+        super().__init__(target, None, 1.0, x0, dim, **k)
+        self.cw_scale = np.broadcast_to(np.asarray(scale, np.float64), (self.dim,)).copy()
+
+    def _configure(self, eng):
+        eng.set_sampler(SAMPLER_CWMH, cw_scale=self.cw_scale)
+
+    def _adapt_window(self, N):
+        return int(0.012 * N)

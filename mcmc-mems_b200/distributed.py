@@ -28,10 +28,20 @@ def half_chain_moments(samples: torch.Tensor) -> torch.Tensor:
     n = samples.shape[0] // 2
     if n < 2:
         raise ValueError("need at least 4 kept draws per chain")
-    halves = torch.stack((samples[:n], samples[-n:]))               # [2, n, P, C]
-    mean = halves.mean(dim=1)                                        # [2, P, C]
-    var = halves.var(dim=1, unbiased=True)
     P = samples.shape[1]
+    if samples.is_cuda:                                              # where the samples live: one CUDA kernel
+        import ctypes as C
+        from . import _lib
+        smp = samples.contiguous().double()
+        out = torch.empty(4, P, smp.shape[2], dtype=torch.float64, device=smp.device)
+        _lib.check(_lib.lib().mems_chain_moments(smp.device.index or 0, C.c_void_p(smp.data_ptr()), smp.shape[0], P,
+                                                 smp.shape[2], C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(smp.device).cuda_stream)), "mems_chain_moments")
+        mean, var = out[0::2], out[1::2]                             # [2, P, C] each
+    else:                                                            # host tensors (gloo tests of the reduction logic)
+        halves = torch.stack((samples[:n], samples[-n:]))            # [2, n, P, C]
+        mean = halves.mean(dim=1)
+        var = halves.var(dim=1, unbiased=True)
     cnt = torch.full((P,), float(2 * samples.shape[2]), dtype=torch.float64, device=samples.device)
     return torch.stack((cnt, mean.sum(dim=(0, 2)), (mean * mean).sum(dim=(0, 2)), var.sum(dim=(0, 2))), dim=1).double()
 
