@@ -49,7 +49,7 @@ typedef struct MemsConfig {
     int32_t n_chains;   /* C: independent chains resident on this device                  */
     int32_t path;       /* MEMS_PATH_FP32 or MEMS_PATH_TC                                 */
     int32_t device;     /* CUDA device ordinal                                            */
-    int32_t chains_per_block; /* 0 = choose; else power of two <= 128                     */
+    int32_t chains_per_block; /* 0 = choose; else 1..128 chains per block batch           */
     int32_t reserved[2];
 } MemsConfig;
 
@@ -171,6 +171,13 @@ int  mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_kee
  * 2: the split chain A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with A = [A_hi; A_lo] (256x64), B = [W_hi; W_lo] (128x64). */
 int  mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev,
                         const void* b_f16_dev, float* d_out_dev, void* stream);
+
+/* Micro-benchmark of the epilogue building blocks (tools/microbench.py).  Modes 0..10 are listed above
+ * microbench_kernel in csrc/mems_tc.cu (tcgen05.ld / tcgen05.st shapes, tanh and split arithmetic).  `blocks`
+ * CTAs of `warps` warps run `iters` repetitions; cycles_out_dev [blocks] i64 = slowest thread of each CTA
+ * (SM clocks), sink_dev [blocks*32*warps] u32 = scratch. */
+int  mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks,
+                     int64_t* cycles_out_dev, uint32_t* sink_dev, void* stream);
 
 /* Number of kernel launches issued through this handle since creation (bench bookkeeping). */
 int64_t mems_launch_count(mems_handle_t h);

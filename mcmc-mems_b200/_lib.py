@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmems_b200.so")
+LIB_PATH = os.environ.get("MEMS_LIB") or os.path.join(_HERE, "libmems_b200.so")   # MEMS_LIB: experimental build
 
 MEMS_PMAX = 4
 MEMS_WIDTH = 64
@@ -24,7 +24,7 @@ SAMPLER_DA = 2
 EXPORTS = [
     "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
     "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
-    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_selftest_umma",
+    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_selftest_umma", "mems_microbench",
 ]
 
 
@@ -73,6 +73,7 @@ def lib():
     L.mems_launch_count.argtypes = [vp]
     L.mems_launch_count.restype = i64
     L.mems_selftest_umma.argtypes = [i32, i32, vp, vp, vp, vp]
+    L.mems_microbench.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
     _lib = L
     return L
 

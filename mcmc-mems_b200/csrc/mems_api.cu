@@ -58,16 +58,8 @@ namespace {
 
 int choose_nc(const MemsHandle_* h, int C) {
     if (h->cfg.chains_per_block > 0) return h->cfg.chains_per_block;
-    if (h->cfg.path == MEMS_PATH_TC) return mems_tc_choose_nc(C, h->host_pb.c.T, h->sm_count);
-    int best = 1;
-    long long best_cost = -1;
-    for (int nc = 1; nc <= MEMS_NCMAX; nc <<= 1) {
-        const long long nbatch = (C + nc - 1) / nc;
-        const long long rounds = (nbatch + h->sm_count - 1) / h->sm_count;
-        const long long cost = rounds * nc;
-        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nc; }
-    }
-    return best;
+    return (h->cfg.path == MEMS_PATH_TC) ? mems_tc_choose_nc(C, h->host_pb.c.T, h->sm_count)
+                                         : mems_fp32_choose_nc(C, h->host_pb.c.T, h->sm_count);
 }
 
 int upload_problem(MemsHandle_* h) {
@@ -105,7 +97,7 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
     if (cfg->path != MEMS_PATH_FP32 && cfg->path != MEMS_PATH_TC) return fail(MEMS_E_INVALID, "unknown path %d", cfg->path);
     if (cfg->chains_per_block != 0) {
         const int v = cfg->chains_per_block;
-        if (v < 1 || v > MEMS_NCMAX || (v & (v - 1))) return fail(MEMS_E_INVALID, "chains_per_block must be a power of two <= %d", MEMS_NCMAX);
+        if (v < 1 || v > MEMS_NCMAX) return fail(MEMS_E_INVALID, "chains_per_block must be in [1,%d]", MEMS_NCMAX);
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -436,6 +428,17 @@ int mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep
     const int e = mems_chain_moments_launch(samples_dev, n_keep, n_params, n_chains, out_dev, prop.multiProcessorCount,
                                             reinterpret_cast<cudaStream_t>(stream));
     if (e != 0) return fail(MEMS_E_CUDA, "chain_moments launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+int mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks, int64_t* cycles_out_dev,
+                    uint32_t* sink_dev, void* stream) {
+    if (!cycles_out_dev || !sink_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (mode < 0 || mode > 10 || warps < 1 || warps > 16 || iters < 1 || blocks < 1) return fail(MEMS_E_INVALID, "bad microbench arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    const int e = mems_tc_microbench(mode, warps, iters, blocks, reinterpret_cast<long long*>(cycles_out_dev), sink_dev,
+                                     reinterpret_cast<cudaStream_t>(stream));
+    if (e != 0) return fail(MEMS_E_CUDA, "microbench launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return MEMS_OK;
 }
 

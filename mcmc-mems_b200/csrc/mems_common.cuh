@@ -79,7 +79,7 @@ struct MemsRunArgs {
     double* loglik_out;                // [n_keep][C] or nullptr
     double* llprop_out;                // explicit mode: [n_steps][n_sub][C] or nullptr
     unsigned char* decisions_out;      // explicit mode: [n_steps][n_sub][C] or nullptr
-    int nc;                            // chains per block batch (power of two <= MEMS_NCMAX)
+    int nc;                            // chains per block batch (1..MEMS_NCMAX)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -410,6 +410,8 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
                     int apply_prior, int t_stride);
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
 int mems_tc_choose_nc(int C, int T, int sm_count);
+int mems_fp32_choose_nc(int C, int T, int sm_count);
+int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st);
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);
 int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned long long step0, int n_steps,
                      double* xi_out, double* log_u_out);

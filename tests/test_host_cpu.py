@@ -28,7 +28,7 @@ def test_abi_argument_errors_without_gpu(lib_built):
     bad = _lib.MemsConfig(9, 150, 4, 0, 0, 0)
     assert L.mems_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert b"n_params" in L.mems_last_error()
-    bad = _lib.MemsConfig(3, 150, 4, 0, 0, 48)
+    bad = _lib.MemsConfig(3, 150, 4, 0, 0, 129)
     assert L.mems_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert L.mems_run(None, 1, 0, 1, None, None, None) == -1
     import torch
