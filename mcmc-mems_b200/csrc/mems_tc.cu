@@ -137,6 +137,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a converged warp (CUTLASS idiom): the warp stays convergent around the elected instruction, so
+// warp-uniform operands remain in uniform registers (no per-lane "waterfall" loop around UTCHMMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -186,6 +194,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
         ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -239,6 +257,87 @@ __device__ __forceinline__ void tanh8(const uint32_t* v, uint64_t (&T)[4]) {
     upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
     upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
     upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
+}
+
+// 2^-|y| for a pair on the FMA pipe (no MUFU): round-to-nearest range reduction with the 1.5*2^23 magic constant,
+// degree-5 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-8, the same grade as ex2.approx), exponent
+// inserted with one integer shift-add per element.  Offloading part of the exponentials relieves the XU pipe, which
+// also executes the F2FP packs (FlashAttention-4 uses the same trick for softmax).
+__device__ __forceinline__ uint64_t ex2_neg_abs_poly2(uint32_t ya, uint32_t yb) {
+    const float wa = fmaxf(-fabsf(__uint_as_float(ya)), -125.0f), wb = fmaxf(-fabsf(__uint_as_float(yb)), -125.0f);
+    const uint64_t w2 = pk(wa, wb);
+    const uint64_t magic2 = pk(12582912.0f, 12582912.0f);
+    const uint64_t r2 = add2(w2, magic2);
+    const uint64_t f2 = sub2(w2, sub2(r2, magic2));
+    uint64_t p2 = pk(0.001327647129073739f, 0.001327647129073739f);
+    p2 = fma2(p2, f2, pk(0.009675540961325169f, 0.009675540961325169f));
+    p2 = fma2(p2, f2, pk(0.05550713092088699f, 0.05550713092088699f));
+    p2 = fma2(p2, f2, pk(0.24022120237350464f, 0.24022120237350464f));
+    p2 = fma2(p2, f2, pk(0.6931469440460205f, 0.6931469440460205f));
+    p2 = fma2(p2, f2, pk(1.0000001192092896f, 1.0000001192092896f));
+    float pa, pb, ra, rb;
+    upk(p2, pa, pb);
+    upk(r2, ra, rb);
+    const float qa = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23));
+    const float qb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23));
+    return pk(qa, qb);
+}
+
+// tanh8 with NPOLY (0..2) of the four element pairs taking their exponential from the FMA pipe.
+template <int NPOLY>
+__device__ __forceinline__ void tanh8_mix(const uint32_t* v, uint64_t (&T)[4]) {
+    uint64_t Q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < NPOLY) Q[i] = ex2_neg_abs_poly2(v[i], v[i + 4]);
+        else Q[i] = pk(ex2_approx(-fabsf(__uint_as_float(v[i]))), ex2_approx(-fabsf(__uint_as_float(v[i + 4]))));
+    }
+    const uint64_t one2 = pk(1.0f, 1.0f);
+    const uint64_t A0 = add2(Q[0], one2), A1 = add2(Q[1], one2), A2 = add2(Q[2], one2), A3 = add2(Q[3], one2);
+    const uint64_t B0 = mul2(A0, A1), B1 = mul2(A2, A3);
+    float Q0, Q1;
+    upk(mul2(B0, B1), Q0, Q1);
+    const float r = rcp_approx(Q0 * Q1);
+    const uint64_t Rq = pk(r * Q1, r * Q0);
+    const uint64_t Rb0 = mul2(Rq, B1), Rb1 = mul2(Rq, B0);
+    const uint64_t two2 = pk(2.0f, 2.0f), m1 = pk(-1.0f, -1.0f);
+    const uint64_t U0 = fma2(mul2(Rb0, A1), two2, m1), U1 = fma2(mul2(Rb0, A0), two2, m1);
+    const uint64_t U2 = fma2(mul2(Rb1, A3), two2, m1), U3 = fma2(mul2(Rb1, A2), two2, m1);
+    float a, b;
+    upk(U0, a, b); T[0] = pk(copysignf(a, __uint_as_float(v[0])), copysignf(b, __uint_as_float(v[4])));
+    upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
+    upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
+    upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
+}
+
+// hi/lo split + pack of eight tanh values (T[i] = (t_i, t_{i+4})) into operand words 4g..4g+3
+__device__ __forceinline__ void split_pack8(const uint64_t (&T)[4], uint32_t* hi2, uint32_t* lo2) {
+    float t[8], h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk(T[i], t[i], t[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk(sub2(T[i], pk(h[i], h[i + 4])), l[i], l[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hi2[i] = pack_half2(h[2 * i], h[2 * i + 1]);
+        lo2[i] = pack_half2(l[2 * i], l[2 * i + 1]);
+    }
+}
+
+// MIX: share of exponentials on the FMA pipe: 0 -> none, 1 -> 1/4, 2 -> 3/8 (groups alternate 2,1 pairs), 3 -> 1/2
+template <int MIX>
+__device__ __forceinline__ void epilogue_split_mix(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint64_t T[4];
+        if (MIX == 0) tanh8_mix<0>(&v[8 * g], T);
+        else if (MIX == 1) tanh8_mix<1>(&v[8 * g], T);
+        else if (MIX == 2) { if (g & 1) tanh8_mix<1>(&v[8 * g], T); else tanh8_mix<2>(&v[8 * g], T); }
+        else tanh8_mix<2>(&v[8 * g], T);
+        split_pack8(T, &hi2[4 * g], &lo2[4 * g]);
+    }
 }
 
 #if MEMS_TANH_GROUP == 4
@@ -366,16 +465,17 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// MMA issuer of one group: for every surrogate pass the workers announce (ctrl_tiles via bar_S) it serves
-// the group's two slots in the fixed order the workers produce them; ctrl_tiles < 0 ends the loop.
+// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues): for every
+// surrogate pass the workers announce (ctrl_tiles via bar_S) it serves the group's two slots in the fixed order
+// the workers produce them; ctrl_tiles < 0 ends the loop.  `g` must be warp-uniform.
 __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
     const uint32_t wimg = smem_u32(sm.wimg);
-    const uint32_t base = sm.tmem_base + (uint32_t)(g * GSLOT * 128);
+    const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
     uint32_t phA = 0, phS = 0;
     for (;;) {
         mbar_wait(&gs.bar_S, phS);
         phS ^= 1u;
-        const int n_tiles = *reinterpret_cast<volatile int*>(&gs.ctrl_tiles);
+        const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
         if (n_tiles < 0) break;
         const int n_pairs = (n_tiles + 1) >> 1;
         for (int pair = 0; pair < n_pairs; ++pair) {
@@ -387,8 +487,11 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                         mbar_wait(&gs.bar_A[s], (phA >> s) & 1u);
                         phA ^= (1u << s);
                         tc_fence_after();
-                        issue_layer(wimg, base + s * 128, layer);
-                        umma_commit(&gs.bar_D[s]);
+                        if (elect_one()) {
+                            issue_layer(wimg, base + s * 128, layer);
+                            umma_commit(&gs.bar_D[s]);
+                        }
+                        __syncwarp();
                     }
                 }
             }
@@ -633,8 +736,8 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NW) {
-        if ((tid & 31) == 0) mma_issuer_loop(sm, gs, g);
-        __syncwarp();
+        const int gw = __shfl_sync(0xffffffffu, (tid - NW) >> 5, 0);     // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
         const int gt = tid & (GT - 1);
         uint32_t phD = 0;
@@ -686,8 +789,8 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
     if (tid >= NW) {
-        if ((tid & 31) == 0) mma_issuer_loop(sm, gs, g);
-        __syncwarp();
+        const int gw = __shfl_sync(0xffffffffu, (tid - NW) >> 5, 0);     // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
         const int gt = tid & (GT - 1);
         uint32_t phD = 0;
@@ -885,7 +988,7 @@ microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
     __syncthreads();
     tc_fence_after();
     const uint32_t base = tbase_s;
-    const uint32_t tl = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) * 64) & 511);
+    const uint32_t tl = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) * 128) & 511);
     uint32_t v[64], hi2[16], lo2[16];
     uint32_t acc = 0;
 #pragma unroll
@@ -899,6 +1002,10 @@ microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
     tc_wait_st();
     __syncthreads();
     const long long t0 = clock64();
+    if (iters & 1) {                       // odd iteration counts: stagger the warps of an SMSP by ~a quarter iteration each
+        const long long until = t0 + (long long)(warp >> 2) * ((MODE == 17) ? 900 : 450);
+        while (clock64() < until) {}
+    }
     if (MODE == 10) {
         for (int it = 0; it < iters; it += 4) {
             tmem_ld32(tl, v);
@@ -935,6 +1042,75 @@ microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
                 tmem_st16(tl + 48, lo2);
                 tc_wait_st();
                 acc ^= hi2[0];
+            } else if (MODE >= 11 && MODE <= 14) {
+                tmem_ld32(tl, v);
+                tc_wait_ld();
+                epilogue_split_mix<MODE - 11>(v, hi2, lo2);
+                tmem_st16(tl + 32, hi2);
+                tmem_st16(tl + 48, lo2);
+                tc_wait_st();
+                acc ^= hi2[0];
+            } else if (MODE == 15 || MODE == 16) {
+                // software pipeline across chunks: exponential/tanh stage of chunk it+1 in the same basic block as the
+                // split/pack/store stage of chunk it (Tc = carried tanh values)
+                uint64_t* Tc = reinterpret_cast<uint64_t*>(v + 32);       // 16 packed pairs = v[32..63]
+                if (it == 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) tanh8_mix<MODE - 15>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                }
+                tmem_ld32(tl, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    split_pack8(*reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]), &hi2[4 * g], &lo2[4 * g]);
+                    tanh8_mix<MODE - 15>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                }
+                tmem_st16(tl + 32, hi2);
+                tmem_st16(tl + 48, lo2);
+                tc_wait_st();
+                acc ^= hi2[0];
+            } else if (MODE == 17) {
+                // one thread owns a full 64-column row: intra-thread software pipeline over the 8 groups of eight
+                tmem_ld32(tl, v);
+                tmem_ld32(tl + 32, v + 32);
+                tc_wait_ld();
+                uint64_t Ta[4], Tb[4];
+                tanh8_mix<0>(&v[0], Ta);
+#pragma unroll
+                for (int g = 0; g < 8; g += 2) {
+                    tanh8_mix<0>(&v[8 * (g + 1)], Tb);
+                    split_pack8(Ta, &hi2[(4 * g) & 15], &lo2[(4 * g) & 15]);
+                    if (g + 2 < 8) tanh8_mix<0>(&v[8 * (g + 2)], Ta);
+                    split_pack8(Tb, &hi2[(4 * g + 4) & 15], &lo2[(4 * g + 4) & 15]);
+                    if (g == 2) { tmem_st16(tl, hi2); tmem_st16(tl + 32, lo2); }
+                }
+                tmem_st16(tl + 16, hi2);
+                tmem_st16(tl + 48, lo2);
+                tc_wait_st();
+                acc ^= hi2[0];
+            } else if (MODE == 18 || MODE == 19) {
+                // chunk of 32 (mode 18) / 64 (mode 19) columns as a ROLLED loop over groups of eight with the tanh values
+                // carried: body = { ld(g+1); split/pack/st(g); wait::ld; tanh(g+1) }
+                constexpr int NG = (MODE == 18) ? 4 : 8;
+                uint64_t T[4];
+                uint32_t w8[8], h4[4], l4[4];
+                tmem_ld8(tl, w8);
+                tc_wait_ld();
+                tanh8_mix<0>(w8, T);
+#pragma unroll 1
+                for (int g = 1; g < NG; ++g) {
+                    tmem_ld8(tl + 8 * g, w8);
+                    split_pack8(T, h4, l4);
+                    tmem_st4(tl + 64 + 4 * (g - 1), h4);
+                    tmem_st4(tl + 96 + 4 * (g - 1), l4);
+                    tc_wait_ld();
+                    tanh8_mix<0>(w8, T);
+                }
+                split_pack8(T, h4, l4);
+                tmem_st4(tl + 64 + 4 * (NG - 1), h4);
+                tmem_st4(tl + 96 + 4 * (NG - 1), l4);
+                tc_wait_st();
+                acc ^= h4[0];
             } else if (MODE == 4) {
                 tmem_ld32(tl, v);
                 tmem_ld32(tl + 32, v + 32);
@@ -1004,6 +1180,111 @@ microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+    }
+}
+
+// Pipe-throughput probes (16 independent dependency chains per thread, `iters` rounds):
+//   20: MUFU.EX2   21: F2FP (cvt.rn.f16x2.f32)   22: MUFU.EX2 + F2FP interleaved   23: FFMA2   24: LOP3
+//   25: MUFU.EX2 + 4 FFMA2 each   26: MUFU.RCP     27: FADD2
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+pipe_probe_kernel(int iters, long long* cycles_out, unsigned int* sink) {
+    const int tid = threadIdx.x;
+    float x[16];
+    uint64_t p[16];
+    uint32_t u[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        x[i] = -0.01f * (float)(i + (tid & 7)) - 0.1f;
+        p[i] = pk(x[i], 0.5f * x[i]);
+        u[i] = 0x3c003c00u + i + tid;
+    }
+    const uint64_t c2 = pk(0.999f, 1.001f), d2 = pk(1e-3f, -1e-3f);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (MODE == 20 || MODE == 22 || MODE == 25) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(x[i]) : "f"(-fabsf(x[i])));
+            if (MODE == 26) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(x[i]) : "f"(x[i]));
+            if (MODE == 21 || MODE == 22) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(__uint_as_float(u[i])), "f"(__uint_as_float(u[i] ^ 0x1000u)));
+            if (MODE == 23) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p[i]) : "l"(p[i]), "l"(c2), "l"(d2));
+            if (MODE == 25) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p[(i + 4 * k) & 15]) : "l"(p[(i + 4 * k) & 15]), "l"(c2), "l"(d2));
+            }
+            if (MODE == 27) asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(p[i]) : "l"(p[i]), "l"(d2));
+            if (MODE == 24) asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(u[i]) : "r"(u[i]), "r"(u[(i + 1) & 15]), "r"(0x5555u));
+        }
+    }
+    const long long t1 = clock64();
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { float a, b; upk(p[i], a, b); acc ^= __float_as_uint(x[i]) ^ u[i] ^ __float_as_uint(a) ^ __float_as_uint(b); }
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+    __shared__ long long tmax;
+    if (tid == 0) tmax = 0;
+    __syncthreads();
+    atomicMax(reinterpret_cast<unsigned long long*>(&tmax), (unsigned long long)(t1 - t0));
+    __syncthreads();
+    if (tid == 0) cycles_out[blockIdx.x] = tmax;
+}
+
+// MMA issue-rate probe: `iters` x 4 back-to-back tcgen05.mma (M=128, N=n, K=16, kind::f16) with the A operand in
+// TMEM (ts != 0) or shared memory; reports SM cycles from first issue to commit completion.
+__global__ void __launch_bounds__(128, 1)
+mma_rate_kernel(int n, int ts, int iters, long long* cycles_out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sB = smem_raw;                    // 32 KB: up to 256 rows x 128 B
+    unsigned char* sA = smem_raw + 4 * BLK;          // 16 KB
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 6 * BLK);
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(smem_raw + 6 * BLK + 16);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 6 * BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) {
+        const uint32_t base = __shfl_sync(0xffffffffu, *tbase, 0);
+        const uint32_t idesc = (1u << 4) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t b = make_desc(smem_u32(sB));
+        const uint64_t a = make_desc(smem_u32(sA));
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ts) {
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                                     ::"r"(base), "r"(base + 256 + 8 * ks), "l"(b + 2 * ks), "r"(idesc), "r"(1u) : "memory");
+                    } else {
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                     ::"r"(base), "l"(a + 2 * ks), "l"(b + 2 * ks), "r"(idesc), "r"(1u) : "memory");
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
+        mbar_wait(bar, 0);
+        const long long t1 = clock64();
+        if (tid == 0) cycles_out[blockIdx.x] = t1 - t0;
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tbase), "r"(512) : "memory");
     }
 }
 
@@ -1149,8 +1430,18 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
 int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st) {
     switch (mode) {
 #define MB_CASE(M) case M: microbench_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
-        MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10)
+        MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10) MB_CASE(11) MB_CASE(12) MB_CASE(13) MB_CASE(14) MB_CASE(15) MB_CASE(16) MB_CASE(17) MB_CASE(18) MB_CASE(19)
 #undef MB_CASE
+#define PP_CASE(M) case M: pipe_probe_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
+        PP_CASE(20) PP_CASE(21) PP_CASE(22) PP_CASE(23) PP_CASE(24) PP_CASE(25) PP_CASE(26) PP_CASE(27)
+#undef PP_CASE
+        case 100: case 101: {          // MMA rate probe: `warps` carries N/8 (8, 16 or 32), mode 100 = A in TMEM, 101 = A in smem
+            const size_t smem = 6 * BLK + 64;
+            cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            mma_rate_kernel<<<blocks, 128, smem, st>>>(warps * 8, mode == 100 ? 1 : 0, iters, cycles_out);
+            break;
+        }
         default: return (int)cudaErrorInvalidValue;
     }
     return (int)cudaGetLastError();
