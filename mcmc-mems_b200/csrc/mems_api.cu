@@ -434,7 +434,7 @@ int mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep
 int mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks, int64_t* cycles_out_dev,
                     uint32_t* sink_dev, void* stream) {
     if (!cycles_out_dev || !sink_dev) return fail(MEMS_E_INVALID, "null argument");
-    if (mode < 0 || ((mode > 19 && mode < 20) || (mode > 27 && mode != 100 && mode != 101)) || warps < 1 || warps > 32 || (mode <= 27 && warps > 16) || iters < 1 || blocks < 1) return fail(MEMS_E_INVALID, "bad microbench arguments");
+    if (mode < 0 || ((mode > 19 && mode < 20) || (mode > 29 && mode != 100 && mode != 101)) || warps < 1 || warps > 32 || (mode <= 29 && warps > 16) || iters < 1 || blocks < 1) return fail(MEMS_E_INVALID, "bad microbench arguments");
     CUDA_TRY(cudaSetDevice(device));
     const int e = mems_tc_microbench(mode, warps, iters, blocks, reinterpret_cast<long long*>(cycles_out_dev), sink_dev,
                                      reinterpret_cast<cudaStream_t>(stream));

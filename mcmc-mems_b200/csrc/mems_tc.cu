@@ -32,6 +32,9 @@
 #ifndef MEMS_EXP_EPI
 #define MEMS_EXP_EPI 0         // != 0: timing experiments with deliberately wrong numerics (never shipped)
 #endif
+#ifndef MEMS_EX2_MIX
+#define MEMS_EX2_MIX 0         // share of exponentials evaluated on the FMA pipe: 0 none, 1 -> 1/4, 2 -> 3/8, 3 -> 1/2
+#endif
 #ifndef MEMS_TANH_GROUP
 #define MEMS_TANH_GROUP 8      // activations sharing one MUFU.RCP: 8 (1.125 MUFU/activation) or 4 (1.25, shorter chain)
 #endif
@@ -393,24 +396,7 @@ __device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2
     }
     return;
 #endif
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint64_t T[4];
-        TANH8(&v[8 * g], T);
-        float t[8], h[8], l[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) upk(T[i], t[i], t[i + 4]);
-        // top 11 significant bits: exactly representable in fp16; the remainder goes to the lo operand
-#pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) upk(sub2(T[i], pk(h[i], h[i + 4])), l[i], l[i + 4]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            hi2[4 * g + i] = pack_half2(h[2 * i], h[2 * i + 1]);
-            lo2[4 * g + i] = pack_half2(l[2 * i], l[2 * i + 1]);
-        }
-    }
+    epilogue_split_mix<MEMS_EX2_MIX>(v, hi2, lo2);
 }
 
 // 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights.
@@ -419,7 +405,7 @@ __device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float*
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         uint64_t T[4];
-        TANH8(&v[8 * g], T);
+        tanh8_mix<(MEMS_EX2_MIX > 0) ? 1 : 0>(&v[8 * g], T);
         const float4 wa = *reinterpret_cast<const float4*>(w7p + 8 * g);
         const float4 wb = *reinterpret_cast<const float4*>(w7p + 8 * g + 4);
         acc = fma2(T[0], pk(wa.x, wa.y), acc);
@@ -975,8 +961,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return y;
 }
 
+#ifndef MEMS_MB_THREADS
+#define MEMS_MB_THREADS 512    // 576 -> the register budget of the product kernel (112 per thread)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(MEMS_MB_THREADS, 1)
 microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
     __shared__ uint32_t tbase_s;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -1111,6 +1100,48 @@ microbench_kernel(int iters, long long* cycles_out, unsigned int* sink) {
                 tmem_st4(tl + 96 + 4 * (NG - 1), l4);
                 tc_wait_st();
                 acc ^= h4[0];
+            } else if (MODE == 29) {
+                // mode 15 with the operand words stored per group of eight (st.x4): shorter live ranges
+                uint64_t* Tc = reinterpret_cast<uint64_t*>(v + 32);
+                if (it == 0) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) tanh8_mix<0>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                }
+                tmem_ld32(tl, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint32_t h4[4], l4[4];
+                    split_pack8(*reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]), h4, l4);
+                    tmem_st4(tl + 64 + 4 * g, h4);
+                    tmem_st4(tl + 96 + 4 * g, l4);
+                    tanh8_mix<0>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                    acc ^= h4[0];
+                }
+                tc_wait_st();
+            } else if (MODE == 28) {
+                // mode 15 at 16-column granularity (2 + 2 groups of eight in flight per thread)
+                uint64_t* Tc = reinterpret_cast<uint64_t*>(v + 32);       // 8 packed pairs
+                if (it == 0) {
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) tanh8_mix<0>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                }
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(tl) : "memory");
+                tc_wait_ld();
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    split_pack8(*reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]), &hi2[4 * g], &lo2[4 * g]);
+                    tanh8_mix<0>(&v[8 * g], *reinterpret_cast<uint64_t(*)[4]>(&Tc[4 * g]));
+                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(tl + 64), "r"(hi2[0]), "r"(hi2[1]), "r"(hi2[2]), "r"(hi2[3]), "r"(hi2[4]), "r"(hi2[5]), "r"(hi2[6]), "r"(hi2[7]) : "memory");
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(tl + 96), "r"(lo2[0]), "r"(lo2[1]), "r"(lo2[2]), "r"(lo2[3]), "r"(lo2[4]), "r"(lo2[5]), "r"(lo2[6]), "r"(lo2[7]) : "memory");
+                tc_wait_st();
+                acc ^= hi2[0];
             } else if (MODE == 4) {
                 tmem_ld32(tl, v);
                 tmem_ld32(tl + 32, v + 32);
@@ -1432,8 +1463,9 @@ int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cy
 #define MB_CASE(M) case M: microbench_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
         MB_CASE(0) MB_CASE(1) MB_CASE(2) MB_CASE(3) MB_CASE(4) MB_CASE(5) MB_CASE(6) MB_CASE(7) MB_CASE(8) MB_CASE(9) MB_CASE(10) MB_CASE(11) MB_CASE(12) MB_CASE(13) MB_CASE(14) MB_CASE(15) MB_CASE(16) MB_CASE(17) MB_CASE(18) MB_CASE(19)
 #undef MB_CASE
+#define MB_CASE(M) case M: microbench_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
 #define PP_CASE(M) case M: pipe_probe_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
-        PP_CASE(20) PP_CASE(21) PP_CASE(22) PP_CASE(23) PP_CASE(24) PP_CASE(25) PP_CASE(26) PP_CASE(27)
+        PP_CASE(20) PP_CASE(21) PP_CASE(22) PP_CASE(23) PP_CASE(24) PP_CASE(25) PP_CASE(26) PP_CASE(27) MB_CASE(28) MB_CASE(29)
 #undef PP_CASE
         case 100: case 101: {          // MMA rate probe: `warps` carries N/8 (8, 16 or 32), mode 100 = A in TMEM, 101 = A in smem
             const size_t smem = 6 * BLK + 64;

@@ -37,6 +37,8 @@ MODES = {
     15: ("pipelined: tanh(next) || split+st(cur)", None, 32),
     16: ("pipelined, 1/4 poly", None, 32),
     17: ("64 cols/thread, intra-thread pipeline", None, 64),
+    28: ("pipelined, 16 cols per iteration", None, 16),
+    29: ("pipelined, st.x4 per group", None, 32),
     18: ("32 cols, rolled 8-col pipeline", None, 32),
     19: ("64 cols, rolled 8-col pipeline", None, 64),
 }
