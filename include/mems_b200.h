@@ -164,6 +164,33 @@ int  mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths,
 int  mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params,
                         int32_t n_chains, double* out_dev, void* stream);
 
+/* Lag-autocovariance sums of kept samples: the sufficient statistics of the (multi-chain) effective sample
+ * size, computed where the samples live.  Replaces the first step of Samples.compute_ess (arviz underneath; call
+ * site tests/Xaccelerometer_geometric/identification.ipynb:308) at scale.
+ * samples_dev [n_keep][P][C] f64 -> out_dev [P][max_lag + 2] f64: for every parameter the SUM over chains of the
+ * biased autocovariance (1/n) sum_k (x_k - m)(x_{k+lag} - m) for lag = 0..max_lag-1, then the sum of the chain
+ * means m and the sum of m^2.  Sums (not means) so that shards on several GPUs combine with one all-reduce.
+ * Deterministic (fixed reduction order).  n_keep <= 20480. */
+int  mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params,
+                        int32_t n_chains, int32_t max_lag, double* out_dev, void* stream);
+
+/* Batched bounded least-squares fit of the surrogate to observed traces: n independent starts advance together.
+ * Replaces least_squares_optimization (src/InverseProblems/utils.py:83-93: scipy least_squares with
+ * jac='3-point' and bounds, then inv(J^T J)), which the notebooks call once per start
+ * (tests/Xaccelerometer_geometric/identification.ipynb:222-227).  Levenberg-Marquardt on the same 3-point
+ * finite-difference Jacobian (step rel_step*max(1,|x|), rel_step = 0 selects scipy's eps^(1/3); one-sided next to
+ * a bound).  With scipy's step the float32 surrogate makes J, and therefore inv(J^T J), noise-dominated (the
+ * reference has the same property); rel_step ~ 3e-4 gives the noise-free covariance.  Every iteration
+ * evaluates the surrogate at the 2P+1 stencil points of every start with the handle's forward kernel.
+ * x0_dev [P][n] f64; yobs_dev [n_obs][T] f64 with n_obs = 1 (shared) or n (one trace per start), NULL = the
+ * handle's y_obs; bounds_lo/hi HOST [P] or NULL = the prior box; stops per start on scipy's xtol / ftol rules or
+ * after max_iter iterations.  Outputs (device): x_out [P][n], cov_out [n][P][P] = inv(J^T J) (may be NULL),
+ * cost_out [n] = 0.5*||f(x)-y||^2 (may be NULL), iters_out [n] accepted steps (may be NULL). */
+int  mems_lsq(mems_handle_t h, const double* x0_dev, int32_t n, const double* yobs_dev, int32_t n_obs,
+              const double* bounds_lo, const double* bounds_hi, int32_t max_iter, double rel_step, double xtol,
+              double ftol, double* x_out_dev, double* cov_out_dev, double* cost_out_dev, int32_t* iters_out_dev,
+              void* stream);
+
 /* Hardware self-test of the tensor-core plumbing the MH kernels rely on (UMMA descriptors,
  * 128B swizzle, TMEM operand packing, tcgen05.ld/st, commit->mbarrier):
  * D[128][64] (f32) = A[128][64] (f16) * B[64][64]^T (f16), all device pointers, row-major.

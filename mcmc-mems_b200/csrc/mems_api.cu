@@ -13,6 +13,12 @@
 int mems_mlp_forward_launch(int n_layers, const int* widths, const float* const* Wd, const float* const* bd,
                             const float* X, long long n, float* Y, int sm_count, cudaStream_t st);
 int mems_chain_moments_launch(const double* samples, int n_keep, int P, int C, double* out, int sm_count, cudaStream_t st);
+size_t mems_lsq_workspace_bytes(int n, int P, int T);
+int mems_lsq_run(const MemsLaunchCtx& ctx, bool use_tc, const double* x0_dev, int n, const double* yobs_dev, int n_obs,
+                 const double* lb_dev, const double* ub_dev, int max_iter, double rel_step, double xtol, double ftol, void* workspace,
+                 double* x_out, double* cov_out, double* cost_out, int* iters_out);
+size_t mems_acov_workspace_bytes(int n_keep, int P, int C, int L);
+int mems_acov_launch(const double* samples, int n_keep, int P, int C, int L, void* workspace, double* out, cudaStream_t st);
 size_t mems_tc_wimg_bytes();
 void mems_tc_build_wimg(const MemsProblem& pb, void* host_img);
 
@@ -428,6 +434,71 @@ int mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep
     const int e = mems_chain_moments_launch(samples_dev, n_keep, n_params, n_chains, out_dev, prop.multiProcessorCount,
                                             reinterpret_cast<cudaStream_t>(stream));
     if (e != 0) return fail(MEMS_E_CUDA, "chain_moments launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+int mems_lsq(mems_handle_t h, const double* x0_dev, int32_t n, const double* yobs_dev, int32_t n_obs,
+             const double* bounds_lo, const double* bounds_hi, int32_t max_iter, double rel_step, double xtol, double ftol,
+             double* x_out_dev, double* cov_out_dev, double* cost_out_dev, int32_t* iters_out_dev, void* stream) {
+    if (!h) return fail(MEMS_E_INVALID, "null handle");
+    if (!h->have_weights || !h->have_problem) return fail(MEMS_E_STATE, "set weights and problem first");
+    if (n < 0 || max_iter < 1) return fail(MEMS_E_INVALID, "need n >= 0 and max_iter >= 1");
+    if (!(rel_step >= 0.0) || rel_step > 0.1) return fail(MEMS_E_INVALID, "rel_step must be in [0, 0.1] (0 = scipy's eps^(1/3))");
+    if (rel_step == 0.0) rel_step = 6.0554544523933395e-06;
+    if (n == 0) return MEMS_OK;
+    if (!x0_dev || !x_out_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (yobs_dev && n_obs != 1 && n_obs != n) return fail(MEMS_E_INVALID, "n_obs must be 1 or n");
+    if ((bounds_lo == nullptr) != (bounds_hi == nullptr)) return fail(MEMS_E_INVALID, "give both bounds or neither");
+    const int P = h->host_pb.c.P, T = h->host_pb.c.T;
+    if ((long long)n * (2 * P + 1) > 2000000000LL) return fail(MEMS_E_INVALID, "too many starts");
+    double b[2 * MEMS_PMAX];
+    for (int p = 0; p < P; ++p) {
+        b[p] = bounds_lo ? bounds_lo[p] : h->host_pb.c.low[p];
+        b[MEMS_PMAX + p] = bounds_hi ? bounds_hi[p] : h->host_pb.c.high[p];
+        if (!(b[p] < b[MEMS_PMAX + p])) return fail(MEMS_E_INVALID, "bounds of parameter %d are empty", p);
+    }
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t wbytes = mems_lsq_workspace_bytes(n, P, T) + 16 * 256;
+    void* ws = nullptr;
+    double* bdev = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws, wbytes, st));
+    cudaError_t e1 = cudaMallocAsync(reinterpret_cast<void**>(&bdev), sizeof(b), st);
+    if (e1 != cudaSuccess) { cudaFreeAsync(ws, st); return fail(MEMS_E_CUDA, "cudaMallocAsync failed: %s", cudaGetErrorString(e1)); }
+    // the bounds travel through pageable memory: cudaMemcpyAsync stages them before returning
+    e1 = cudaMemcpyAsync(bdev, b, sizeof(b), cudaMemcpyHostToDevice, st);
+    int rc = MEMS_OK;
+    if (e1 != cudaSuccess) rc = fail(MEMS_E_CUDA, "cudaMemcpyAsync failed: %s", cudaGetErrorString(e1));
+    if (rc == MEMS_OK) {
+        MemsLaunchCtx ctx = make_ctx(h, stream);
+        const int e = mems_lsq_run(ctx, h->cfg.path == MEMS_PATH_TC, x0_dev, n, yobs_dev ? yobs_dev : h->dev_yobs,
+                                   yobs_dev ? n_obs : 1, bdev, bdev + MEMS_PMAX, max_iter, rel_step, xtol, ftol, ws, x_out_dev, cov_out_dev,
+                                   cost_out_dev, iters_out_dev);
+        h->launches += 3LL * max_iter + 2;
+        if (e != 0) rc = fail(MEMS_E_CUDA, "least-squares launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    }
+    cudaFreeAsync(bdev, st);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+int mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params, int32_t n_chains,
+                       int32_t max_lag, double* out_dev, void* stream) {
+    if (!samples_dev || !out_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (n_keep < 4 || n_params < 1 || n_chains < 1) return fail(MEMS_E_INVALID, "need n_keep >= 4, n_params >= 1, n_chains >= 1");
+    if (max_lag < 1 || max_lag > n_keep) return fail(MEMS_E_INVALID, "max_lag must be in [1, n_keep]");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t wbytes = mems_acov_workspace_bytes(n_keep, n_params, n_chains, max_lag);
+    if (wbytes == 0) return fail(MEMS_E_INVALID, "n_keep=%d too long for the shared-memory autocovariance kernel (max 20480)", n_keep);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    void* ws = nullptr;
+    CUDA_TRY(cudaMallocAsync(&ws, wbytes, st));
+    const int e = mems_acov_launch(samples_dev, n_keep, n_params, n_chains, max_lag, ws, out_dev, st);
+    cudaFreeAsync(ws, st);
+    if (e != 0) return fail(MEMS_E_CUDA, "autocovariance launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return MEMS_OK;
 }
 

@@ -71,6 +71,50 @@ def _ess(a):
     return total / tau
 
 
+def ess_classic(chains):
+    """Multi-chain ESS of [chain, draw] without splitting or rank-normalisation (the at-scale form)."""
+    return _ess(np.atleast_2d(np.asarray(chains, np.float64)))
+
+
+def ess_from_autocov(acov_mean, n_draws: int, n_chains: int, chain_mean_var: float):
+    """The same estimator as :func:`_ess` from its sufficient statistics: ``acov_mean[t]`` = mean over chains of
+    the biased lag-t autocovariance (t < L), ``chain_mean_var`` = unbiased variance of the chain means.
+    Returns ``(ess, truncated)``; ``truncated`` is True when Geyer's sequence had not turned negative by lag L."""
+    acov = np.asarray(acov_mean, np.float64)
+    n, L = int(n_draws), len(acov)
+    mean_var = acov[0] * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n
+    if n_chains > 1:
+        var_plus += chain_mean_var
+    rho = np.zeros(L + 2)
+    even = 1.0
+    rho[0] = even
+    odd = 1.0 - (mean_var - acov[1]) / var_plus
+    rho[1] = odd
+    t = 1
+    limit = min(n - 3, L - 2)
+    while t < limit and even + odd > 0.0:
+        even = 1.0 - (mean_var - acov[t + 1]) / var_plus
+        odd = 1.0 - (mean_var - acov[t + 2]) / var_plus
+        if even + odd >= 0:
+            rho[t + 1], rho[t + 2] = even, odd
+        t += 2
+    truncated = bool(even + odd > 0.0 and limit < n - 3)
+    max_t = t - 2
+    if even > 0:
+        rho[max_t + 1] = even
+    t = 1
+    while t <= max_t - 2:
+        if rho[t + 1] + rho[t + 2] > rho[t - 1] + rho[t]:
+            rho[t + 1] = (rho[t - 1] + rho[t]) / 2.0
+            rho[t + 2] = rho[t + 1]
+        t += 2
+    total = n_chains * n
+    tau = -1.0 + 2.0 * rho[:max_t + 1].sum() + rho[max_t + 1:max_t + 2].sum()
+    tau = max(tau, 1.0 / np.log10(total))
+    return total / tau, truncated
+
+
 def ess_bulk(chains):
     """chains: [chain, draw] of one scalar parameter -> bulk ESS (arviz ``method='bulk'``)."""
     return _ess(_z_scale(_split_chains(np.atleast_2d(np.asarray(chains, np.float64)))))

@@ -89,3 +89,37 @@ def gather_samples(samples: torch.Tensor, group: Optional[dist.ProcessGroup] = N
     out = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:s] for o, s in zip(out, sizes)]).permute(1, 2, 0).contiguous()
+
+
+def ess(samples: torch.Tensor, max_lag: int = 0, group: Optional[dist.ProcessGroup] = None):
+    """Multi-chain effective sample size per parameter over every chain of every rank.
+
+    The lag-autocovariance sums are computed on the device that holds the shard (``mems_chain_autocov``), one
+    all-reduce of ``P*(max_lag+2)+1`` doubles combines the ranks, Geyer's truncation runs on the host on a vector
+    of ``max_lag`` numbers.  Same estimator as arviz's ``ess`` without rank-normalisation (``diagnostics.ess_classic``).
+    Returns ``(ess [P] numpy, truncated [P] bool)``."""
+    import numpy as np
+    from . import diagnostics
+    n, P, C_local = samples.shape
+    L = int(max_lag) if max_lag else min(n, 1024)
+    if samples.is_cuda:
+        from .engine import chain_autocov
+        sums = chain_autocov(samples, L)
+    else:                                                            # host tensors: gloo tests of the reduction logic
+        x = samples.double()
+        c = x - x.mean(dim=0, keepdim=True)
+        ac = torch.stack([(c[:n - t] * c[t:]).sum(dim=0).sum(dim=1) / n for t in range(L)], dim=1)      # [P, L]
+        m = x.mean(dim=0)                                            # [P, C]
+        sums = torch.cat((ac, m.sum(dim=1, keepdim=True), (m * m).sum(dim=1, keepdim=True)), dim=1)
+    flat = torch.cat((sums.reshape(-1), torch.tensor([float(C_local)], dtype=torch.float64, device=sums.device)))
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat = flat.cpu().numpy()
+    Ct = int(round(flat[-1]))
+    tab = flat[:-1].reshape(P, L + 2)
+    out, trunc = np.zeros(P), np.zeros(P, bool)
+    for p in range(P):
+        s1, s2 = tab[p, L], tab[p, L + 1]
+        var_m = (s2 - s1 * s1 / Ct) / (Ct - 1.0) if Ct > 1 else 0.0
+        out[p], trunc[p] = diagnostics.ess_from_autocov(tab[p, :L] / Ct, n, Ct, var_m)
+    return out, trunc

@@ -171,6 +171,37 @@ class MHEngine:
         _lib.check(self._L.mems_forward(self._h, _ptr(xt), n, _ptr(y), _ptr(ll), _stream(self.device)), "mems_forward")
         return y, ll
 
+    # -- least-squares initialisation ---------------------------------------------
+    def least_squares(self, starts, y_obs=None, bounds=None, max_iter: int = 60, rel_step: float = 0.0,
+                      xtol: float = 1e-8, ftol: float = 1e-8):
+        """Fit every start point at once (``mems_lsq``).  starts: [n, P]; y_obs: None (the problem's trace),
+        [T] or [n, T]; bounds: None (prior box) or (low[P], high[P]); rel_step: finite-difference step relative
+        to max(1,|x|) (0 = scipy's eps^(1/3), the reference's setting; ~3e-4 removes the float32 noise from J).
+        Returns device tensors (x_opt [n, P], cov [n, P, P] = inv(J^T J), cost [n], iters [n])."""
+        xd = self._dev(starts).reshape(-1, self.P)
+        n = xd.shape[0]
+        xt = xd.t().contiguous()
+        yd, n_obs = None, 1
+        if y_obs is not None:
+            yd = self._dev(y_obs).reshape(-1, self.T).contiguous()
+            n_obs = yd.shape[0]
+            if n_obs not in (1, n):
+                raise ValueError("y_obs must be [T] or [n, T]")
+        lo = hi = None
+        if bounds is not None:
+            lo, hi = _host(bounds[0]), _host(bounds[1])
+            if lo.shape != (self.P,) or hi.shape != (self.P,):
+                raise ValueError("bounds must be (low[P], high[P])")
+        xo = self._new(self.P, n)
+        cov = self._new(n, self.P, self.P)
+        cost = self._new(n)
+        its = self._new(n, dtype=torch.int32)
+        _lib.check(self._L.mems_lsq(self._h, _ptr(xt), n, _ptr(yd), n_obs,
+                                    None if lo is None else lo.ctypes.data, None if hi is None else hi.ctypes.data,
+                                    int(max_iter), float(rel_step), float(xtol), float(ftol), _ptr(xo), _ptr(cov), _ptr(cost), _ptr(its),
+                                    _stream(self.device)), "mems_lsq")
+        return xo.t().contiguous(), cov, cost, its
+
     # -- sampler variant ---------------------------------------------------------
     def set_sampler(self, sampler: int, cw_scale=None, da_stride: int = 4):
         """SAMPLER_MH (reference), SAMPLER_CWMH (component-wise; ``cw_scale[P]`` = initial per-component
@@ -248,6 +279,19 @@ class MHEngine:
     @property
     def launches(self) -> int:
         return int(self._L.mems_launch_count(self._h))
+
+
+def chain_autocov(samples: torch.Tensor, max_lag: int) -> torch.Tensor:
+    """samples [n_keep, P, C] f64 on a CUDA device -> [P, max_lag + 2] sums over chains (``mems_chain_autocov``)."""
+    if not samples.is_cuda:
+        raise MemsError("chain_autocov needs device samples (no CPU fallback)")
+    smp = samples.contiguous().double()
+    n_keep, P, Cn = smp.shape
+    out = torch.empty(P, max_lag + 2, dtype=torch.float64, device=smp.device)
+    dev = smp.device.index or 0
+    _lib.check(_lib.lib().mems_chain_autocov(dev, _ptr(smp), n_keep, P, Cn, int(max_lag), _ptr(out), _stream(dev)),
+               "mems_chain_autocov")
+    return out
 
 
 def mlp_forward(layers, X, device: int = 0):

@@ -61,3 +61,43 @@ def least_squares_optimization(y_observed, forward_model, start_point, bounds):
     res = least_squares(objective_function, start_point, args=(np.asarray(y_observed), forward_model),
                         bounds=bounds, jac="3-point")
     return res.x, np.linalg.inv(res.jac.T @ res.jac)
+
+
+def batched_least_squares(y_observed, forward_model, start_points, bounds, sigma2: float = 1.0, path: int = PATH_FP32,
+                          device: int = 0, max_iter: int = 60, rel_step: float = 0.0):
+    """All start points (and optionally one observed trace per start) fitted together on the GPU.
+
+    Same contract as calling :func:`least_squares_optimization` in a loop, as the notebooks do
+    (tests/Xaccelerometer_geometric/identification.ipynb:222-227): returns ``(x_opts [n,P], covs [n,P,P])`` with
+    ``covs[i] = inv(J^T J)`` at the optimum of start ``i``.  ``y_observed`` is ``[T]`` or ``[n,T]``.
+    """
+    spec = forward_model.spec
+    P, T = spec.n_params, spec.n_time
+    starts = np.asarray(start_points, np.float64).reshape(-1, P)
+    y = np.asarray(y_observed, np.float64).reshape(-1, T)
+    lo, hi = np.asarray(bounds[0], np.float64), np.asarray(bounds[1], np.float64)
+    eng = MHEngine(spec, y[0], sigma2, lo, hi, np.eye(P), n_chains=1, path=path, device=device)
+    try:
+        x, cov, _, _ = eng.least_squares(starts, y_obs=None if y.shape[0] == 1 else y, bounds=(lo, hi), max_iter=max_iter,
+                                           rel_step=rel_step)
+        return x.cpu().numpy(), cov.cpu().numpy()
+    finally:
+        eng.close()
+
+
+def sensitivity_push_forward(sample, model, scaler, S_avg: float = 4.44):
+    """Posterior push-forward through the sensitivity surrogate -- the computation inside
+    ``plot_sensitivity_histogram`` (src/InverseProblems/plotsPaper.py:201-210) without the plot.
+
+    ``sample``: ``(P, Ns)`` like ``Samples.samples`` (or ``(C, P, Ns)`` for batched chains); ``model``: an
+    ``NN_Model`` / ``DenseStack`` (inference on the GPU); ``scaler``: the fitted scaler of the sensitivity data set.
+    Returns ``dict(values, mean, ci_lower, ci_upper)`` with the 5 % / 95 % percentiles the reference shades.
+    """
+    a = np.asarray(getattr(sample, "samples", sample), np.float64)
+    if a.ndim == 3:
+        a = np.moveaxis(a, 1, 0).reshape(a.shape[1], -1)          # (C, P, Ns) -> (P, C*Ns)
+    rows = scaler.transform(a.T)
+    net = getattr(model, "model", model)
+    values = np.asarray(net.predict(rows)).reshape(-1) / S_avg
+    lo, hi = np.percentile(values, [5, 95])
+    return {"values": values, "mean": float(values.mean()), "ci_lower": float(lo), "ci_upper": float(hi)}

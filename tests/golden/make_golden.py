@@ -109,7 +109,28 @@ def k1_fft():
              tf_pred=tf_pred, y_test=y_test, **pack_layers(layers))
 
 
+def sensitivity():
+    """Sensitivity surrogate of the geometric test (config_II.json: 3 -> 32x4 tanh -> 1) with its data split and
+    scaler -- the inputs of plot_sensitivity_histogram (src/InverseProblems/plotsPaper.py:201-210; call site
+    tests/Xaccelerometer_geometric/identification.ipynb:586-588)."""
+    tdir = os.path.join(REF, "tests", "Xaccelerometer_geometric")
+    cwd = os.getcwd()
+    os.chdir(tdir)
+    try:
+        dp = preprocessing("./config_II.json")
+        layers = layers_of(dp.config["MODEL_PATH"])
+    finally:
+        os.chdir(cwd)
+    np.savez(os.path.join(HERE, "sensitivity.npz"), scaler_mean=dp.scaler.mean_, scaler_scale=dp.scaler.scale_,
+             X_test=dp.X_test[:64], y_test=np.asarray(dp.y_test[:64], np.float64).reshape(-1),
+             X_test_scaled=dp.X_test_scaled[:64], **pack_layers(layers))
+
+
 def main():
+    if "--sensitivity-only" in sys.argv:
+        sensitivity()
+        return
+    sensitivity()
     geo_bounds = ([0.1, -0.5, 29.0], [0.5, 0.5, 31.0])          # geometric cell 6
     geo_starts = [[0.3, 0.0, 30.0], [0.4, 0.25, 30.0], [0.2, 0.25, 30.0],
                   [0.4, -0.25, 30.0], [0.2, -0.25, 30.0]]

@@ -26,7 +26,8 @@ def _worker(rank, world, port, ret):
         rhat = D.split_rhat(mine)
         mean, std = D.posterior_moments(mine)
         gathered = D.gather_samples(mine)
-        ret[rank] = (rhat.numpy(), mean.numpy(), std.numpy(), gathered.numpy(), full.numpy(), (c0, c1))
+        ess, trunc = D.ess(mine, max_lag=n_keep)
+        ret[rank] = (rhat.numpy(), mean.numpy(), std.numpy(), gathered.numpy(), full.numpy(), (c0, c1), ess, trunc)
     finally:
         dist.destroy_process_group()
 
@@ -51,6 +52,9 @@ def test_two_rank_gloo_sharding_rhat_and_gather():
         want = diagnostics.split_rhat_from_moments(halves.mean(axis=1), halves.var(axis=1, ddof=1), n)
         assert r0[0][p] == pytest.approx(want, rel=1e-12) and r1[0][p] == pytest.approx(want, rel=1e-12)
     assert r0[0][2] > 1.2 and abs(r0[0][0] - 1) < 0.1
+    for p in range(3):                                       # ESS over all chains of both ranks == single-process estimator
+        want = diagnostics.ess_classic(full[:, p, :].T)
+        assert r0[6][p] == pytest.approx(want, rel=1e-10) and r1[6][p] == pytest.approx(want, rel=1e-10)
 
 
 def test_shard_range_covers_everything():

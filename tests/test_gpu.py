@@ -482,3 +482,120 @@ def test_cuqi_cwmh_and_da_lookalikes():
     assert s.samples.shape == (8, 3, 1000) and np.all(s.acc_rate > 0.05)
     d = DelayedAcceptanceMH(post, Gaussian(np.zeros(3), pb["cov"]), x0=pb["x_opts"][0], seed=4, stride=3).sample_adapt(800, 0)
     assert d.samples.shape == (3, 800) and 0.0 < d.acc_rate < 0.5
+
+
+# ----------------------------------------------------------------------------- rows either side of the path
+def test_autocov_kernel_and_device_ess():
+    from mcmc_mems_b200 import diagnostics as D, distributed
+    from mcmc_mems_b200.engine import chain_autocov
+    rng = np.random.default_rng(5)
+    n, P, Cn = 600, 3, 37
+    x = np.zeros((n, P, Cn))
+    rho = np.array([0.0, 0.6, 0.9])[None, :, None]
+    for k in range(1, n):
+        x[k] = rho[0] * x[k - 1] + rng.standard_normal((P, Cn))
+    x[:, 1, :] += 5.0
+    smp = torch.as_tensor(x, device="cuda")
+    L = 256
+    got = chain_autocov(smp, L).cpu().numpy()
+    for p in range(P):
+        chains = x[:, p, :].T                                                   # [chain, draw]
+        want = D._autocov(chains)[:, :L].sum(axis=0)
+        assert np.allclose(got[p, :L], want, rtol=1e-9, atol=1e-9)
+        m = chains.mean(axis=1)
+        assert got[p, L] == pytest.approx(m.sum(), rel=1e-12) and got[p, L + 1] == pytest.approx((m * m).sum(), rel=1e-12)
+    ess, trunc = distributed.ess(smp, max_lag=L)
+    for p in range(P):
+        assert not trunc[p]
+        assert ess[p] == pytest.approx(D.ess_classic(x[:, p, :].T), rel=1e-8)
+    assert ess[0] > 3 * ess[1] > 3 * ess[2]
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_batched_least_squares_matches_scipy_fixture(path):
+    """mems_lsq against the fixture produced by scipy least_squares(jac='3-point') on the oracle
+    (tests/golden/make_golden.py, following identification.ipynb:222-227): same optima, same inv(J^T J)."""
+    pb = helpers.load_problem("geometric")
+    eng = helpers.engine(pb, 1, path)
+    # scipy's step (6e-6 relative) is only meaningful on the FP32 check path, whose outputs carry ~2e-6 relative
+    # noise; the split-FP16 tensor-core path (<= 1.1e-5) needs the wider step from the start
+    x, cov, cost, its = eng.least_squares(pb["starts"], rel_step=0.0 if path == 0 else 3e-4)
+    torch.cuda.synchronize()
+    x, cov, cost, its = x.cpu().numpy(), cov.cpu().numpy(), cost.cpu().numpy(), its.cpu().numpy()
+    post_std = np.sqrt(np.diag(pb["cov"] * pb["sigma2"]))
+    assert np.all(its >= 2)
+    # The valley is flat along the thickness: scipy's own five optima scatter by ~0.4 posterior std and their costs by
+    # 5.6e-4 relative (float32 surrogate under 3-point differences: both optimisers stop at the noise floor of the
+    # finite-difference gradient).  Parity = inside that scatter; the cost bound 2e-3 is 0.14 nats of log-likelihood.
+    fwd = helpers.oracle_forward(pb)
+    ref_cost = np.array([0.5 * np.sum((fwd(xo) - pb["y_obs"]) ** 2) for xo in pb["x_opts"]])
+    centre, spread = pb["x_opts"].mean(axis=0), np.ptp(pb["x_opts"], axis=0)
+    for i in range(len(pb["starts"])):
+        assert np.all(np.abs(x[i] - centre) < spread + 0.5 * post_std), (i, x[i], centre)
+        assert 0.5 * np.sum((fwd(x[i]) - pb["y_obs"]) ** 2) < ref_cost.max() * (1 + 2e-3), (i, its[i], cost[i])
+    # Covariance.  With scipy's step (6e-6 relative) the float32 surrogate makes the finite-difference Jacobian, and
+    # with it inv(J^T J), noise-dominated: scipy's own result varies 3.1..3.8 (thickness variance) across the five
+    # starts against 4.87 for a noise-free Jacobian.  Default step: same order as the fixture (the reference's
+    # behaviour); rel_step = 3e-4: the noise-free value, checked against float64 central differences of the oracle.
+    ref = pb["cov"]
+    d_ref = np.diag(ref)
+    for i in range(len(pb["starts"])):
+        assert np.all(np.diag(cov[i]) > 0.4 * d_ref) and np.all(np.diag(cov[i]) < 2.5 * d_ref), (i, np.diag(cov[i]), d_ref)   # noqa: E501
+        assert np.allclose(cov[i], cov[i].T, rtol=1e-9, atol=0)
+    x2, cov2, _, _ = eng.least_squares(pb["starts"], rel_step=3e-4)
+    x2, cov2 = x2.cpu().numpy(), cov2.cpu().numpy()
+    from oracle import batched_forward
+    for i in range(len(pb["starts"])):
+        h = 1e-4 * np.maximum(1.0, np.abs(x2[i]))
+        J = np.stack([(batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], (x2[i] + h[q] * np.eye(3)[q])[None], np.float64)[0]
+                       - batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], (x2[i] - h[q] * np.eye(3)[q])[None], np.float64)[0]) / (2 * h[q])
+                      for q in range(3)], axis=1)
+        exact = np.linalg.inv(J.T @ J)
+        assert np.allclose(cov2[i], exact, rtol=0.08, atol=0.03 * np.sqrt(np.outer(np.diag(exact), np.diag(exact)))), (i, cov2[i], exact)
+        assert np.all(np.abs(x2[i] - centre) < spread + 0.5 * post_std)
+    assert np.allclose(cost, ref_cost.mean(), rtol=2e-3)
+    eng.close()
+
+
+def test_batched_least_squares_many_observations_and_bounds():
+    """One trace per start (the 'many observations' use) and a start whose optimum sits on a bound."""
+    from oracle import batched_forward
+    pb = helpers.load_problem("geometric")
+    rng = np.random.default_rng(11)
+    n = 24
+    truth = rng.uniform(pb["low"] + 0.1 * (pb["high"] - pb["low"]), pb["high"] - 0.1 * (pb["high"] - pb["low"]), size=(n, 3))
+    Y = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], truth).astype(np.float64)
+    eng = helpers.engine(pb, 1, 0)
+    starts = np.tile(0.5 * (pb["low"] + pb["high"]), (n, 1))
+    x, cov, cost, _ = eng.least_squares(starts, y_obs=Y, max_iter=80)
+    x, cost = x.cpu().numpy(), cost.cpu().numpy()
+    ok = cost < 1e-3                                            # noise-free traces: the fit is exact where it converged
+    assert ok.mean() > 0.8
+    assert np.allclose(x[ok][:, :2], truth[ok][:, :2], atol=2e-3)
+    # bounds: shrink the box so that the truth of trace 0 lies outside -> the fit stops on the face
+    hi = pb["high"].copy()
+    hi[0] = truth[0, 0] - 0.02
+    xb, _, _, _ = eng.least_squares(starts[:1], y_obs=Y[:1], bounds=(pb["low"], hi))
+    xb = xb.cpu().numpy()[0]
+    assert xb[0] == pytest.approx(hi[0], abs=1e-9) and np.all(xb >= pb["low"]) and np.all(xb <= hi)
+    eng.close()
+
+
+def test_sensitivity_push_forward_matches_oracle():
+    import os
+    from mcmc_mems_b200 import NN_Model, FixtureProcessor, sensitivity_push_forward
+    from oracle.surrogate import mlp_forward as np_mlp
+    d = np.load(os.path.join(helpers.GOLDEN, "sensitivity.npz"))
+    layers = helpers.layers_of(d)
+    net = NN_Model()
+    net.set_layers(layers)
+    dp = FixtureProcessor(np.zeros(1), d["scaler_mean"], d["scaler_scale"])
+    pin = helpers.pins()["geometric_sample_10"]
+    rng = np.random.default_rng(0)
+    sample = np.asarray(pin["mean"])[:, None] + np.asarray(pin["std"])[:, None] * rng.standard_normal((3, 1000))
+    out = sensitivity_push_forward(sample, net, dp.scaler)
+    want = np_mlp(layers, ((sample.T - d["scaler_mean"]) / d["scaler_scale"]).astype(np.float32)).reshape(-1) / 4.44
+    assert np.allclose(out["values"], want, rtol=2e-5, atol=1e-6)
+    assert out["ci_lower"] < out["mean"] < out["ci_upper"]
+    batched = sensitivity_push_forward(np.stack([sample, sample]), net, dp.scaler)      # (C, P, Ns)
+    assert batched["values"].shape == (2000,) and batched["mean"] == pytest.approx(out["mean"], rel=1e-6)

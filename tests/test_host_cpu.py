@@ -135,3 +135,37 @@ def test_diagnostics_on_ar1():
     hm = np.array([c[:n // 2].mean() for c in x] + [c[n // 2:].mean() for c in x])
     hv = np.array([c[:n // 2].var(ddof=1) for c in x] + [c[n // 2:].var(ddof=1) for c in x])
     assert abs(diagnostics.split_rhat_from_moments(hm, hv, n // 2) - 1) < 0.01
+
+
+def test_ess_from_autocov_equals_the_full_estimator():
+    """The at-scale ESS (sufficient statistics -> Geyer on the host) is the same estimator as the full-sample one."""
+    from mcmc_mems_b200 import diagnostics as D
+    rng = np.random.default_rng(3)
+    n_chain, n = 6, 800
+    x = np.zeros((n_chain, n))
+    for k in range(1, n):
+        x[:, k] = 0.8 * x[:, k - 1] + rng.standard_normal(n_chain)
+    want = D.ess_classic(x)
+    acov = D._autocov(x).mean(axis=0)
+    got, trunc = D.ess_from_autocov(acov, n, n_chain, x.mean(axis=1).var(ddof=1))
+    assert not trunc and got == pytest.approx(want, rel=1e-12)
+    got2, trunc2 = D.ess_from_autocov(acov[:200], n, n_chain, x.mean(axis=1).var(ddof=1))     # lags cut at 200: enough for rho=0.8
+    assert not trunc2 and got2 == pytest.approx(want, rel=1e-12)
+    _, trunc3 = D.ess_from_autocov(acov[:4], n, n_chain, x.mean(axis=1).var(ddof=1))          # too few lags: flagged
+    assert trunc3
+    assert 0.05 * n_chain * n < want < 0.25 * n_chain * n                                   # (1-rho)/(1+rho) = 0.11
+
+
+def test_sensitivity_fixture_and_push_forward_math():
+    """Pin the sensitivity surrogate (config_II) the push-forward uses: the numpy restatement of the Keras stack
+    reproduces the held-out targets of the reference's own split to surrogate accuracy."""
+    import helpers
+    from oracle.surrogate import mlp_forward
+    d = np.load(os.path.join(helpers.GOLDEN, "sensitivity.npz"))
+    layers = helpers.layers_of(d)
+    assert [k.shape for k, _, _ in layers] == [(3, 32), (32, 32), (32, 32), (32, 32), (32, 1)]
+    rows = (d["X_test"] - d["scaler_mean"]) / d["scaler_scale"]
+    assert np.allclose(rows, d["X_test_scaled"], rtol=0, atol=1e-12)
+    pred = mlp_forward(layers, rows.astype(np.float32)).reshape(-1)
+    rel = np.abs(pred - d["y_test"]) / np.abs(d["y_test"])
+    assert np.median(rel) < 0.01 and rel.max() < 0.05
