@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/microbench.py 11,15,18,19 > gpurun_out/microbench9.log 2>&1
+echo "mb rc=$?"; grep "^mode" gpurun_out/microbench9.log
