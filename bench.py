@@ -45,6 +45,19 @@ def load_peaks():
     return 1590.0, 1400.0, 6650.0, "fallback"
 
 
+def measured_traffic(args):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), when it was taken on
+    this workload; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "r01_bench_kernel_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    if (d.get("workload"), d.get("chains"), d.get("mh_updates_per_launch"), d.get("thin")) != \
+            (args.workload, args.chains, args.inner, args.thin) or args.path != "tc":
+        return None
+    return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+
+
 def problem(name, T_override=None):
     import helpers
     pb = helpers.load_problem(name)
@@ -307,7 +320,9 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                         "frac": achieved / peak_burst, "traffic": None, "peak_source": f"{which} burst bf16",
+                         "frac": achieved / peak_burst, "traffic": measured_traffic(args),
+                         "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_bench_kernel_traffic.json)",
+                         "peak_source": f"{which} burst bf16",
                          "frac_of_sustained": achieved / peak_sust,
                          "issued_mma_frac": (achieved * (3.0 * 5 * 64 * 64 + 5 * 16 * 64 + 32 * 64) / (5 * 64 * 64 + (P + 1) * 64 + 64)) / peak_burst
                          if path == PATH_TC else 0.0,
