@@ -200,7 +200,7 @@ int  mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev,
                         const void* b_f16_dev, float* d_out_dev, void* stream);
 
 /* Micro-benchmark of the epilogue building blocks (tools/microbench.py).  Modes 0..10 are listed above
- * microbench_kernel in csrc/mems_tc.cu (tcgen05.ld / tcgen05.st shapes, tanh and split arithmetic).  `blocks`
+ * the kernels in csrc/mems_microbench.cu (tcgen05.ld / tcgen05.st shapes, tanh and split arithmetic).  `blocks`
  * CTAs of `warps` warps run `iters` repetitions; cycles_out_dev [blocks] i64 = slowest thread of each CTA
  * (SM clocks), sink_dev [blocks*32*warps] u32 = scratch. */
 int  mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks,

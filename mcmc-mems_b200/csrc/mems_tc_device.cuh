@@ -1,0 +1,356 @@
+// Device-side building blocks of the tensor-core path (sm_100a): shared-memory image layout, PTX wrappers
+// (mbarrier, tcgen05.mma / ld / st / commit, bulk copy), packed FP32x2 arithmetic and the tanh / split epilogue math.
+// Included by mems_tc.cu (product kernels) and mems_microbench.cu (measurement kernels); everything lives in an
+// anonymous namespace, so each translation unit gets its own copy.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "mems_common.cuh"
+
+#ifndef MEMS_TRYWAIT_HINT
+#define MEMS_TRYWAIT_HINT 0
+#endif
+#ifndef MEMS_EXP_EPI
+#define MEMS_EXP_EPI 0         // != 0: timing experiments with deliberately wrong numerics (never shipped)
+#endif
+#ifndef MEMS_EX2_MIX
+#define MEMS_EX2_MIX 0         // share of exponentials evaluated on the FMA pipe: 0 none, 1 -> 1/4, 2 -> 3/8, 3 -> 1/2
+#endif
+
+namespace {
+
+// CTA organisation: two independent worker groups; each owns one batch of chains at a time, two TMEM
+// tile slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and its own MMA
+// issuer warp.  Groups never synchronise with each other, so one group's accept/reject section
+// overlaps the other group's tensor work.
+constexpr int NGROUP = 2;
+constexpr int GSLOT = 2;                       // tile slots per group
+// NH = worker warps per TMEM lane quarter: 1 -> a thread owns a whole 64-column row of the tile,
+// 2 -> two threads split the row (32 columns each), doubling the warps the scheduler can interleave.
+__host__ __device__ constexpr int gthreads(int NH) { return 128 * NH; }                 // worker threads per group
+__host__ __device__ constexpr int nworker(int NH) { return NGROUP * gthreads(NH); }
+__host__ __device__ constexpr int nthreads(int NH) { return nworker(NH) + 32 * NGROUP; } // + one MMA issuer warp per group
+constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
+constexpr int BLK_B1 = 0;             // layer-1 B operand
+constexpr int BLK_WHI = 1;            // 5 blocks
+constexpr int BLK_WLO = 6;            // 5 blocks
+constexpr int BLK_BIAS = 11;          // 2 blocks: hidden layer h<4 at k-step h of block 0, h=4 at k-step 0 of block 1
+constexpr int BLK_ONES = 13;          // 2 blocks = 128 rows of [1,1,1,0,...]
+constexpr int NBLK = 15;
+constexpr int WIMG_TAIL = 64 * 4 + 16;                 // w7[64] f32, b7 f32, pad
+constexpr int WIMG_BYTES = NBLK * BLK + WIMG_TAIL;
+constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
+
+// instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct GroupSmem {
+    ChainBatch cb;
+    double Spart[128];
+    float xchg[GSLOT][128];            // NH=2: partial output-layer dot of the upper column half
+    unsigned long long bar_A[GSLOT];   // workers -> MMA issuer: A operand of the slot is in TMEM
+    unsigned long long bar_D[GSLOT];   // tensor core -> workers: accumulator of the slot is complete
+    unsigned long long bar_X[GSLOT][4]; // NH=2: upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
+    unsigned long long bar_S;          // workers -> MMA issuer: ctrl_tiles of the next pass is valid
+    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
+    int pad_;
+};
+
+struct TcSmem {
+    __align__(1024) unsigned char wimg[NBLK * BLK];
+    float w7[64];
+    float b7;
+    float pad_[3];
+    MemsConsts c;
+    GroupSmem grp[NGROUP];
+    unsigned long long bar_w;
+    uint32_t tmem_base;
+    uint32_t pad2_;
+    // followed by: double yobs[T]; float ts[T];
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(void* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+#if MEMS_TRYWAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint
+#else
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");   // hardware-suspended wait, wakes on completion
+#endif
+    return ok != 0;
+}
+// Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// one lane of a converged warp (CUTLASS idiom): the warp stays convergent around the elected instruction, so
+// warp-uniform operands remain in uniform registers (no per-lane "waterfall" loop around UTCHMMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row atoms
+    d |= (uint64_t)1 << 46;                 // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(void* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);   // .x (low 16 bits) = lo
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// packed FP32x2 arithmetic (FADD2 / FMUL2 / FFMA2): two lanes of work per issue slot
+__device__ __forceinline__ uint64_t pk(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// tanh of eight accumulator values that already hold y = 2*log2(e)*z  (tanh8_mix below):
+//     q = 2^-|y| in (0, 1],   |tanh z| = (1 - q)/(1 + q) = 2/(1 + q) - 1,   sign from y.
+// Because 1 + q lies in (1, 2] the eight denominators can be inverted with ONE MUFU.RCP (product tree,
+// no overflow, no clamp): 1.125 MUFU ops per activation.  Pairs are (element i, element i+4) so that every
+// level of the tree is a packed FMUL2 with no register shuffles.  Results: T[i] = (t_i, t_{i+4}).
+
+// 2^-|y| for a pair on the FMA pipe (no MUFU): round-to-nearest range reduction with the 1.5*2^23 magic constant,
+// degree-5 minimax polynomial of 2^f on [-0.5, 0.5] (max rel. error 7.5e-8, the same grade as ex2.approx), exponent
+// inserted with one integer shift-add per element.  Offloading part of the exponentials relieves the XU pipe, which
+// also executes the F2FP packs (FlashAttention-4 uses the same trick for softmax).
+__device__ __forceinline__ uint64_t ex2_neg_abs_poly2(uint32_t ya, uint32_t yb) {
+    const float wa = fmaxf(-fabsf(__uint_as_float(ya)), -125.0f), wb = fmaxf(-fabsf(__uint_as_float(yb)), -125.0f);
+    const uint64_t w2 = pk(wa, wb);
+    const uint64_t magic2 = pk(12582912.0f, 12582912.0f);
+    const uint64_t r2 = add2(w2, magic2);
+    const uint64_t f2 = sub2(w2, sub2(r2, magic2));
+    uint64_t p2 = pk(0.001327647129073739f, 0.001327647129073739f);
+    p2 = fma2(p2, f2, pk(0.009675540961325169f, 0.009675540961325169f));
+    p2 = fma2(p2, f2, pk(0.05550713092088699f, 0.05550713092088699f));
+    p2 = fma2(p2, f2, pk(0.24022120237350464f, 0.24022120237350464f));
+    p2 = fma2(p2, f2, pk(0.6931469440460205f, 0.6931469440460205f));
+    p2 = fma2(p2, f2, pk(1.0000001192092896f, 1.0000001192092896f));
+    float pa, pb, ra, rb;
+    upk(p2, pa, pb);
+    upk(r2, ra, rb);
+    const float qa = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ra) << 23));
+    const float qb = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(rb) << 23));
+    return pk(qa, qb);
+}
+
+// tanh8 with NPOLY (0..2) of the four element pairs taking their exponential from the FMA pipe.
+template <int NPOLY>
+__device__ __forceinline__ void tanh8_mix(const uint32_t* v, uint64_t (&T)[4]) {
+    uint64_t Q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < NPOLY) Q[i] = ex2_neg_abs_poly2(v[i], v[i + 4]);
+        else Q[i] = pk(ex2_approx(-fabsf(__uint_as_float(v[i]))), ex2_approx(-fabsf(__uint_as_float(v[i + 4]))));
+    }
+    const uint64_t one2 = pk(1.0f, 1.0f);
+    const uint64_t A0 = add2(Q[0], one2), A1 = add2(Q[1], one2), A2 = add2(Q[2], one2), A3 = add2(Q[3], one2);
+    const uint64_t B0 = mul2(A0, A1), B1 = mul2(A2, A3);
+    float Q0, Q1;
+    upk(mul2(B0, B1), Q0, Q1);
+    const float r = rcp_approx(Q0 * Q1);
+    const uint64_t Rq = pk(r * Q1, r * Q0);
+    const uint64_t Rb0 = mul2(Rq, B1), Rb1 = mul2(Rq, B0);
+    const uint64_t two2 = pk(2.0f, 2.0f), m1 = pk(-1.0f, -1.0f);
+    const uint64_t U0 = fma2(mul2(Rb0, A1), two2, m1), U1 = fma2(mul2(Rb0, A0), two2, m1);
+    const uint64_t U2 = fma2(mul2(Rb1, A3), two2, m1), U3 = fma2(mul2(Rb1, A2), two2, m1);
+    float a, b;
+    upk(U0, a, b); T[0] = pk(copysignf(a, __uint_as_float(v[0])), copysignf(b, __uint_as_float(v[4])));
+    upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
+    upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
+    upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
+}
+
+// hi/lo split + pack of eight tanh values (T[i] = (t_i, t_{i+4})) into operand words 4g..4g+3
+__device__ __forceinline__ void split_pack8(const uint64_t (&T)[4], uint32_t* hi2, uint32_t* lo2) {
+    float t[8], h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk(T[i], t[i], t[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __uint_as_float(__float_as_uint(t[i]) & 0xFFFFE000u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk(sub2(T[i], pk(h[i], h[i + 4])), l[i], l[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        hi2[i] = pack_half2(h[2 * i], h[2 * i + 1]);
+        lo2[i] = pack_half2(l[2 * i], l[2 * i + 1]);
+    }
+}
+
+// MIX: share of exponentials on the FMA pipe: 0 -> none, 1 -> 1/4, 2 -> 3/8 (groups alternate 2,1 pairs), 3 -> 1/2
+template <int MIX>
+__device__ __forceinline__ void epilogue_split_mix(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint64_t T[4];
+        if (MIX == 0) tanh8_mix<0>(&v[8 * g], T);
+        else if (MIX == 1) tanh8_mix<1>(&v[8 * g], T);
+        else if (MIX == 2) { if (g & 1) tanh8_mix<1>(&v[8 * g], T); else tanh8_mix<2>(&v[8 * g], T); }
+        else tanh8_mix<2>(&v[8 * g], T);
+        split_pack8(T, &hi2[4 * g], &lo2[4 * g]);
+    }
+}
+
+// 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
+__device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
+#if MEMS_EXP_EPI == 1      // timing experiment only (wrong numerics): MUFU.TANH + one pack, no lo operand
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float a, b;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(__uint_as_float(v[2 * i])));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(__uint_as_float(v[2 * i + 1])));
+        hi2[i] = pack_half2(a, b);
+        lo2[i] = 0u;
+    }
+    return;
+#elif MEMS_EXP_EPI == 2    // timing experiment only: split + pack without tanh
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float t0_ = __uint_as_float(v[2 * i]), t1_ = __uint_as_float(v[2 * i + 1]);
+        const float h0 = __uint_as_float(v[2 * i] & 0xFFFFE000u), h1 = __uint_as_float(v[2 * i + 1] & 0xFFFFE000u);
+        float l0, l1;
+        upk(sub2(pk(t0_, t1_), pk(h0, h1)), l0, l1);
+        hi2[i] = pack_half2(h0, h1);
+        lo2[i] = pack_half2(l0, l1);
+    }
+    return;
+#endif
+    epilogue_split_mix<MEMS_EX2_MIX>(v, hi2, lo2);
+}
+
+// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights.
+// w7p holds the weights permuted per group of eight as (w0,w4, w1,w5, w2,w6, w3,w7) to match tanh8's pairing.
+__device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float* w7p, uint64_t acc) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        uint64_t T[4];
+        tanh8_mix<(MEMS_EX2_MIX > 0) ? 1 : 0>(&v[8 * g], T);
+        const float4 wa = *reinterpret_cast<const float4*>(w7p + 8 * g);
+        const float4 wb = *reinterpret_cast<const float4*>(w7p + 8 * g + 4);
+        acc = fma2(T[0], pk(wa.x, wa.y), acc);
+        acc = fma2(T[1], pk(wa.z, wa.w), acc);
+        acc = fma2(T[2], pk(wb.x, wb.y), acc);
+        acc = fma2(T[3], pk(wb.z, wb.w), acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void split3(float v, float& h, float& m, float& l) {
+    h = __half2float(__float2half_rn(v));
+    const float r1 = v - h;
+    m = __half2float(__float2half_rn(r1));
+    l = r1 - m;
+}
+
+
+}  // namespace
