@@ -115,36 +115,30 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
 template <int NH>
 __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, gthreads(NH)); }
 
-// group barrier + OR-reduction of a predicate over the group's worker threads
-template <int NH>
-__device__ __forceinline__ bool group_any(int g, bool pred) {
-    uint32_t out;
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
-        "barrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(out) : "r"((uint32_t)pred), "r"(1 + g), "r"(gthreads(NH)) : "memory");
-    return out != 0;
-}
-
 // The worker threads of group g evaluate one batch.  Thread (row, h) owns TMEM lane `row` of both slots and
-// columns [64/NH * h, 64/NH * (h+1)) of it; row `row` of every tile is (chain j = row mod nc, time sub-row row / nc).
+// columns [64/NH * h, 64/NH * (h+1)) of it; row `row` of every tile is (chain slot row mod nce, time sub-row row / nce).
+// compact: only the gs.nlive chains listed in gs.map take part (nce = gs.nlive): proposals outside the prior box and,
+// in the delayed-acceptance second stage, proposals the first stage did not promote cost nothing -- the tiles are
+// rebuilt from the live chains, so the pass shrinks with the promotion rate.  Result: gs.Sfin[chain].
 template <int P, int NH>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
-                                              bool skip_dead, float* y_out, int c0, uint32_t& phD) {
+                                              bool compact, float* y_out, int c0, uint32_t& phD) {
     constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
     const int gt = threadIdx.x & (gthreads(NH) - 1);
     const int row = gt & 127;
     const int h = gt >> 7;                            // column half (always 0 when NH == 1)
     const int q = row >> 5;
-    const int j = row % nc;                           // nc is any value in 1..128: rows >= nc*tpt of a tile idle
-    const int sub = row / nc;
-    const int tpt = 128 / nc;                         // time points per tile
+    const int nce = compact ? gs.nlive : nc;          // chains laid out in the tiles (any value in 1..128)
+    const int jc = row % nce;                         // rows >= nce*tpt of a tile idle
+    const int sub = row / nce;
+    const int tpt = 128 / nce;                        // time points per tile
+    const int j = compact ? (int)gs.map[jc] : jc;     // batch-local chain index
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
     const int n_tiles = (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
-    const bool chain_live = (j < ncv) && (sub < tpt) && (!skip_dead || gs.cb.live[j]);
+    const bool chain_live = (sub < tpt) && (compact || jc < ncv);
     if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
         *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
         mbar_arrive(&gs.bar_S);
@@ -155,7 +149,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
 #pragma unroll
-        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (j < ncv) ? gs.cb.xs[p][j] : 0.0f);
+        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
         set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
         set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
         set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
@@ -251,11 +245,31 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     }
     if (h == 0) gs.Spart[row] = Sp;
     group_bar_sync<NH>(g);
-    if (gt < nc) {
+    if (gt < nce) {
         double S = 0.0;                                // fixed order: time sub-rows ascending
-        for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nc + gt];
-        gs.Spart[gt] = S;   // thread gt only ever reads slots {u*nc + gt}: no cross-thread hazard
+        for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
+        gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
     }
+    group_bar_sync<NH>(g);                             // Sfin[chain] may have been written by another thread
+}
+
+// Compaction of the chains that need the coming pass: gs.map / gs.nlive (first warp of the group; ballot prefix sums).
+template <int NH>
+__device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt, int ncv) {
+    group_bar_sync<NH>(g);                             // live[] of every chain is written
+    if (gt < 32) {
+        int base = 0;
+#pragma unroll
+        for (int c = 0; c < MEMS_NCMAX / 32; ++c) {
+            const int jj = 32 * c + gt;
+            const bool lv = jj < ncv && gs.cb.live[jj] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, lv);
+            if (lv) gs.map[base + __popc(m & ((1u << gt) - 1u))] = (unsigned char)jj;
+            base += __popc(m);
+        }
+        if (gt == 0) gs.nlive = base;
+    }
+    group_bar_sync<NH>(g);
 }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
@@ -336,13 +350,14 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
             for (int s = 0; s < ra.n_steps; ++s) {
                 for (int sub = 0; sub < ra.n_sub; ++sub) {
                     if (gt < ncv) batch_pre(gs.cb, sm.c, ch, ra, c0, gt, s, sub);
-                    // barrier + "does any chain of the batch need this pass?" (all proposals outside the prior box,
-                    // or no proposal promoted by the DA first stage -> the pass is skipped entirely)
-                    const bool any = group_any<NH>(g, gt < ncv && gs.cb.live[gt]);
+                    // only the chains that need this pass are laid out in tiles (proposals outside the prior box and
+                    // proposals the DA first stage did not promote drop out); no live chain -> the pass is skipped
+                    group_compact_live<NH>(gs, g, gt, ncv);
+                    const bool any = gs.nlive > 0;
                     if (any)
                         tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, ncv, true,
                                              nullptr, c0, phD);
-                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, any ? gs.Spart[gt] : 0.0);
+                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt]) ? gs.Sfin[gt] : 0.0);
                 }
             }
             batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
@@ -400,7 +415,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
             if (gt < ncv && ll_out) {
                 // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
                 const int Tn = (T + stride - 1) / stride;
-                const double ll = sm.c.neg_half_inv_sigma2 * gs.Spart[gt] * ((double)T / (double)Tn);
+                const double ll = sm.c.neg_half_inv_sigma2 * gs.Sfin[gt] * ((double)T / (double)Tn);
                 ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
             }
         }

@@ -57,7 +57,9 @@ struct GroupSmem {
     unsigned long long bar_X[GSLOT][4]; // NH=2: upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
     unsigned long long bar_S;          // workers -> MMA issuer: ctrl_tiles of the next pass is valid
     int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
-    int pad_;
+    int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
+    double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
+    unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
 };
 
 struct TcSmem {
