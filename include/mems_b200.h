@@ -94,7 +94,9 @@ int  mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out,
  *         is the initial per-component proposal std; adaptation target 0.21/P + 0.23.
  *   DA:   stage 1 scores every da_stride-th time point (log-likelihood rescaled by T/Tc) and promotes
  *         with log u1 <= min(0, lc* - lc); stage 2 (promoted only) scores all T points and accepts
- *         with log u2 <= min(0, (l* - l) - (lc* - lc)).  A pass no chain of a batch needs is skipped.
+ *         with log u2 <= min(0, (l* - l) - (lc* - lc)).  da_stride = 0 selects the FFT coarse surrogate as stage 1
+ *         instead (mems_set_coarse_fft).  Every pass lays out only the chains that need it (inside the prior box;
+ *         stage 2: promoted), so stage 2 costs in proportion to the promotion rate.
  * Call before mems_init_chains.  With n_sub = 1 (MH), P (CWMH), 2 (DA) the per-update arrays of
  * mems_run_explicit / mems_draw become log_u [n_steps][n_sub][C], loglik_prop_out and
  * decisions_out [n_steps][n_sub][C]; for CWMH xi holds the standard normals z, not chol*z. */
@@ -102,6 +104,16 @@ int  mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out,
 #define MEMS_SAMPLER_CWMH 1
 #define MEMS_SAMPLER_DA   2
 int  mems_set_sampler(mems_handle_t h, int32_t sampler, const double* cw_scale, int32_t da_stride);
+
+/* Coarse first-stage model of delayed acceptance: the reference's FFT surrogate (models/model_VoltageSignal_fft.keras,
+ * trained on the features of src/utils/preprocessing.py:90-103 -- [10*mean, |F_1..7|, 100*angle(F_1..7)] of the trace),
+ * turned back into a band-limited trace with the reference's reconstruction
+ * (tests/Xaccelerometer_quality_factor/surrogate_fft.ipynb cell 15) and scored against the problem's y_obs with the
+ * problem's sigma2.  One surrogate row per proposal instead of T.
+ * W/b: HOST pointer arrays of the 7 Dense layers (Keras layout, [P][64], 5 x [64][64], [64][15]); scaler_mean/scale
+ * HOST [P] (the StandardScaler of the FFT model's inputs, parameters only).  Then mems_set_sampler(h, DA, NULL, 0). */
+int  mems_set_coarse_fft(mems_handle_t h, const float* const* W, const float* const* b,
+                         const double* scaler_mean, const double* scaler_scale);
 
 /* Chain initialisation.  Replaces MH(target, proposal, x0) + the first lines of
  * cuqi MH._sample_adapt (samples[:,0]=x0, target_eval[0]=logd(x0), acc[0]=1, scale=0.1):

@@ -51,6 +51,10 @@ struct MemsHandle_ {
     float* dev_ts = nullptr;
     double* dev_yobs = nullptr;
     void* dev_wimg = nullptr;
+    MemsCoarse* dev_coarse = nullptr;      // FFT coarse surrogate of delayed acceptance (device copy)
+    MemsCoarse* host_coarse = nullptr;
+    bool have_coarse = false, use_coarse = false;
+    std::vector<double> host_yobs;
     MemsChains chains;
     bool have_weights = false, have_problem = false, have_chains = false;
     int sampler = MEMS_MODE_RW;
@@ -73,6 +77,28 @@ int upload_problem(MemsHandle_* h) {
     h->host_pb.yobs = h->dev_yobs;
     h->host_pb.wimg = reinterpret_cast<const uint4*>(h->dev_wimg);
     CUDA_TRY(cudaMemcpy(h->dev_pb, &h->host_pb, sizeof(MemsProblem), cudaMemcpyHostToDevice));
+    return MEMS_OK;
+}
+
+// projections of y_obs on the first harmonics of the uniform grid (coarse_fft_pass), then the device copy
+int upload_coarse(MemsHandle_* h) {
+    if (!h->have_coarse || h->host_yobs.empty()) return MEMS_OK;
+    MemsCoarse& cm = *h->host_coarse;
+    const int T = h->host_pb.c.T;
+    const double two_pi = 6.283185307179586476925286766559;
+    cm.sum_y2 = cm.sum_y = 0.0;
+    for (int t = 0; t < T; ++t) { cm.sum_y2 += h->host_yobs[t] * h->host_yobs[t]; cm.sum_y += h->host_yobs[t]; }
+    for (int k = 1; k <= MEMS_COARSE_HARM; ++k) {
+        double c = 0.0, sn = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const double a = two_pi * (double)k * (double)t / (double)T;
+            c += h->host_yobs[t] * cos(a);
+            sn += h->host_yobs[t] * sin(a);
+        }
+        cm.cy[k - 1] = c;
+        cm.sy[k - 1] = sn;
+    }
+    CUDA_TRY(cudaMemcpy(h->dev_coarse, h->host_coarse, sizeof(MemsCoarse), cudaMemcpyHostToDevice));
     return MEMS_OK;
 }
 
@@ -158,6 +184,8 @@ void mems_destroy(mems_handle_t h) {
     cudaFree(h->chains.win_acc); cudaFree(h->chains.adapt_i); cudaFree(h->chains.acc_count);
     cudaFree(h->chains.scale_cw); cudaFree(h->chains.lambda_cw); cudaFree(h->chains.win_cw);
     cudaFree(h->chains.llc); cudaFree(h->chains.prom_count);
+    cudaFree(h->dev_coarse);
+    delete h->host_coarse;
     delete h;
 }
 
@@ -209,7 +237,10 @@ int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_m
     for (int t = 0; t < T; ++t) ts[t] = (float)((time[t] - scaler_mean[P]) / scaler_scale[P]);
     CUDA_TRY(cudaMemcpy(h->dev_ts, ts.data(), sizeof(float) * T, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(h->dev_yobs, y_obs, sizeof(double) * T, cudaMemcpyHostToDevice));
+    h->host_yobs.assign(y_obs, y_obs + T);
     h->have_problem = true;
+    const int rc = upload_coarse(h);                       // the coarse stage scores the same observation
+    if (rc != MEMS_OK) return rc;
     return upload_problem(h);
 }
 
@@ -260,12 +291,55 @@ int mems_set_sampler(mems_handle_t h, int32_t sampler, const double* cw_scale, i
         }
     }
     if (sampler == MEMS_MODE_DA) {
-        if (da_stride < 1 || da_stride > h->host_pb.c.T) return fail(MEMS_E_INVALID, "da_stride=%d outside [1,T]", da_stride);
-        h->da_stride = da_stride;
+        if (da_stride == 0) {                              // coarse stage = the FFT surrogate
+            if (!h->have_coarse) return fail(MEMS_E_STATE, "da_stride = 0 selects the FFT coarse surrogate: call mems_set_coarse_fft first");
+            h->use_coarse = true;
+            h->da_stride = 1;
+        } else {
+            if (da_stride < 1 || da_stride > h->host_pb.c.T) return fail(MEMS_E_INVALID, "da_stride=%d outside [0,T]", da_stride);
+            h->use_coarse = false;
+            h->da_stride = da_stride;
+        }
     }
     h->sampler = sampler;
     h->have_chains = false;     // chains must be (re)initialised for the new sampler
     return MEMS_OK;
+}
+
+int mems_set_coarse_fft(mems_handle_t h, const float* const* W, const float* const* b, const double* scaler_mean,
+                        const double* scaler_scale) {
+    if (!h || !W || !b || !scaler_mean || !scaler_scale) return fail(MEMS_E_INVALID, "null argument");
+    for (int i = 0; i < MEMS_HIDDEN + 1; ++i)
+        if (!W[i] || !b[i]) return fail(MEMS_E_INVALID, "null weight pointer for layer %d", i);
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const int P = h->host_pb.c.P;
+    if (!h->host_coarse) {
+        h->host_coarse = new (std::nothrow) MemsCoarse();
+        if (!h->host_coarse) return fail(MEMS_E_CUDA, "out of host memory");
+    }
+    if (!h->dev_coarse) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->dev_coarse), sizeof(MemsCoarse)));
+    MemsCoarse& cm = *h->host_coarse;
+    memset(&cm, 0, sizeof(cm));
+    memcpy(cm.W1, W[0], sizeof(float) * P * MEMS_WIDTH);                 // Keras layout [in][out], in = P (no time column)
+    memcpy(cm.b1, b[0], sizeof(float) * MEMS_WIDTH);
+    for (int l = 0; l < MEMS_NLAYER_H; ++l) {
+        memcpy(cm.Wh + l * MEMS_WIDTH * MEMS_WIDTH, W[1 + l], sizeof(float) * MEMS_WIDTH * MEMS_WIDTH);
+        memcpy(cm.bh + l * MEMS_WIDTH, b[1 + l], sizeof(float) * MEMS_WIDTH);
+    }
+    for (int k = 0; k < MEMS_WIDTH; ++k)
+        for (int o = 0; o < MEMS_COARSE_OUT; ++o) cm.Wo[k * 16 + o] = W[MEMS_HIDDEN][k * MEMS_COARSE_OUT + o];
+    for (int o = 0; o < MEMS_COARSE_OUT; ++o) cm.bo[o] = b[MEMS_HIDDEN][o];
+    for (int p = 0; p < P; ++p) {
+        if (!(scaler_scale[p] != 0.0)) return fail(MEMS_E_INVALID, "scaler_scale[%d] is zero", p);
+        cm.mean[p] = scaler_mean[p];
+        cm.sscale[p] = scaler_scale[p];
+    }
+    if (h->host_pb.c.T < 2 * MEMS_COARSE_HARM + 1)
+        return fail(MEMS_E_INVALID, "the FFT coarse surrogate needs n_time >= %d", 2 * MEMS_COARSE_HARM + 1);
+    h->have_coarse = true;
+    h->have_chains = false;
+    if (h->host_yobs.empty()) CUDA_TRY(cudaMemcpy(h->dev_coarse, h->host_coarse, sizeof(MemsCoarse), cudaMemcpyHostToDevice));
+    return upload_coarse(h);
 }
 
 int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint64_t seed, uint64_t chain_id0,
@@ -290,8 +364,9 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
                : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.ll, 1, 1);
     h->launches += 2;
     if (e == 0 && h->sampler == MEMS_MODE_DA) {   // coarse log-likelihood of the start state
-        e = tc ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride)
-               : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride);
+        if (h->use_coarse) e = mems_coarse_ll_launch(ctx, h->dev_coarse, h->chains.x, C, h->chains.llc);
+        else e = tc ? mems_tc_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride)
+                    : mems_fp32_forward(ctx, h->chains.x, C, nullptr, h->chains.llc, 1, h->da_stride);
         h->launches += 1;
     }
     if (e != 0) return fail(MEMS_E_CUDA, "init launch failed: %s", cudaGetErrorString((cudaError_t)e));
@@ -306,6 +381,7 @@ static int run_common(mems_handle_t h, MemsRunArgs& ra, void* stream) {
     ra.mode = h->sampler;
     ra.n_sub = (h->sampler == MEMS_MODE_CW) ? h->host_pb.c.P : (h->sampler == MEMS_MODE_DA ? 2 : 1);
     ra.da_stride = h->da_stride;
+    ra.coarse = (h->sampler == MEMS_MODE_DA && h->use_coarse) ? h->dev_coarse : nullptr;
     ra.target_acc = (h->sampler == MEMS_MODE_CW) ? 0.21 / h->host_pb.c.P + 0.23 : 0.234;
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_run(ctx, ra) : mems_fp32_run(ctx, ra);

@@ -43,6 +43,27 @@ struct MemsProblem {
     const uint4* wimg;                                 // tensor-core path: pre-swizzled fp16 weight image
 };
 
+// Coarse first-stage surrogate of delayed acceptance: the reference's FFT model (model_VoltageSignal_fft.keras,
+// src/utils/preprocessing.py:90-103: P -> 64x6 tanh -> 15 features = [10*mean, |F_1..7|, 100*angle(F_1..7)] of the trace)
+// turned back into a band-limited trace by the reference's own reconstruction
+// (tests/Xaccelerometer_quality_factor/surrogate_fft.ipynb cell 15):
+//     y_c[t] = m + (2/T) sum_k A_k cos(2 pi k t / T + phi_k),  m = 0.1 f_0,  A_k = f_k,  phi_k = 0.01 f_{7+k}
+// and scored against the same observation with the same noise variance.  Because the harmonics are orthogonal on the
+// uniform grid, ||y_obs - y_c||^2 needs only 2*7+2 projections of y_obs (computed once on the host).
+#define MEMS_COARSE_OUT 15
+#define MEMS_COARSE_HARM 7
+struct MemsCoarse {
+    float W1[MEMS_PMAX * MEMS_WIDTH];                  // [P][64]: parameters only, no time column
+    float b1[MEMS_WIDTH];
+    __align__(16) float Wh[MEMS_NLAYER_H * MEMS_WIDTH * MEMS_WIDTH];
+    float bh[MEMS_NLAYER_H * MEMS_WIDTH];
+    float Wo[MEMS_WIDTH * 16];                         // [64][15], rows padded to 16
+    float bo[16];
+    double mean[MEMS_PMAX], sscale[MEMS_PMAX];         // StandardScaler of the coarse model's inputs
+    double sum_y2, sum_y;                              // sum y_obs^2, sum y_obs
+    double cy[MEMS_COARSE_HARM], sy[MEMS_COARSE_HARM]; // sum_t y_obs[t] cos / sin(2 pi k t / T), k = 1..7
+};
+
 // Mutable chain state, SoA over chains.
 struct MemsChains {
     int C;
@@ -71,6 +92,7 @@ struct MemsRunArgs {
     int mode;                          // MEMS_MODE_*
     int n_sub;                         // surrogate evaluations per update: 1 (RW), P (CW), 2 (DA)
     int da_stride;                     // DA: the coarse stage scores every da_stride-th time point
+    const MemsCoarse* coarse;          // DA: non-null -> the coarse stage is the FFT surrogate instead (da_stride unused)
     double target_acc;                 // adaptation target: 0.234 (RW), 0.21/P + 0.23 (CW)
     unsigned long long step0;          // updates already done (global sample index of the state)
     const double* xi;                  // explicit mode: [n_steps][P][C] (RW/DA: chol*z; CW: z), else nullptr
@@ -168,7 +190,7 @@ struct ChainBatch {
     unsigned int acc_count[MEMS_NCMAX];
     unsigned int prom_count[MEMS_NCMAX];
     unsigned char inb[MEMS_NCMAX];        // proposal inside the prior box
-    unsigned char live[MEMS_NCMAX];       // rows of this chain must be evaluated in the coming pass
+    unsigned char live[MEMS_NCMAX];       // 1: rows of this chain must be evaluated in the coming pass (2: see DA stage 1)
 };
 
 __device__ __forceinline__ void batch_load(ChainBatch& cb, const MemsChains& ch, int P, int mode, int c0, int j, int ncv) {
@@ -276,6 +298,90 @@ __device__ __forceinline__ void batch_pre(ChainBatch& cb, const MemsConsts& pb, 
     // DA, sub == 1: xs unchanged; live[] was set by the first-stage decision
 }
 
+// DA with the FFT coarse surrogate: pass `sub` == 0 does not go through the trace surrogate at all
+__device__ __forceinline__ bool batch_pass_is_coarse_model(const MemsRunArgs& ra, int sub) {
+    return ra.mode == MEMS_MODE_DA && sub == 0 && ra.coarse != nullptr;
+}
+
+// Coarse squared misfit S_c[j] = ||y_obs - y_c(x_j)||^2 of `n` points, evaluated cooperatively by `nthr` threads
+// (a multiple of 64; thread t owns neuron t%64 of two points per chunk of 2*nthr/64 points).
+//   x[p*xstride + idx]: unscaled parameters;  map: optional list of point indices (nullptr = 0..n-1);
+//   S[idx] receives the result;  act: scratch of 2*(2*nthr/64)*64 floats;  bar(): barrier over the nthr threads.
+template <class Bar>
+__device__ __forceinline__ void coarse_fft_pass(const MemsCoarse* __restrict__ cm, int P, int T, const double* x, int xstride,
+                                                const unsigned char* map, int n, double* S, float* act, int t, int nthr, Bar bar) {
+    const int nn = t & 63, cg = t >> 6, ngrp = nthr >> 6, CH = 2 * ngrp;
+    float* bufA = act;
+    float* bufB = act + CH * MEMS_WIDTH;
+    for (int base = 0; base < n; base += CH) {
+        bar();
+        if (t < CH * MEMS_PMAX) {                          // scaled inputs (utils.py:38-39 convention: f64 scale, f32 cast)
+            const int c = t / MEMS_PMAX, p = t % MEMS_PMAX;
+            float v = 0.0f;
+            if (base + c < n && p < P) {
+                const int idx = map ? (int)map[base + c] : base + c;
+                v = (float)((x[(size_t)p * xstride + idx] - cm->mean[p]) / cm->sscale[p]);
+            }
+            bufB[c * MEMS_WIDTH + p] = v;
+        }
+        bar();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {                      // layer 1: P -> 64
+            const int c = cg + u * ngrp;
+            float z = bufB[c * MEMS_WIDTH] * __ldg(&cm->W1[nn]);
+            for (int p = 1; p < P; ++p) z = fmaf(bufB[c * MEMS_WIDTH + p], __ldg(&cm->W1[p * MEMS_WIDTH + nn]), z);
+            bufA[c * MEMS_WIDTH + nn] = tanhf(z + __ldg(&cm->b1[nn]));
+        }
+        bar();
+        float* in = bufA;
+        float* out = bufB;
+#pragma unroll 1
+        for (int l = 0; l < MEMS_NLAYER_H; ++l) {          // 64 -> 64
+            const float* W = cm->Wh + l * MEMS_WIDTH * MEMS_WIDTH;
+            const float* a0 = in + cg * MEMS_WIDTH;
+            const float* a1 = in + (cg + ngrp) * MEMS_WIDTH;
+            float z0 = 0.0f, z1 = 0.0f;
+#pragma unroll 8
+            for (int k = 0; k < MEMS_WIDTH; ++k) {
+                const float w = __ldg(&W[k * MEMS_WIDTH + nn]);
+                z0 = fmaf(a0[k], w, z0);
+                z1 = fmaf(a1[k], w, z1);
+            }
+            const float b = __ldg(&cm->bh[l * MEMS_WIDTH + nn]);
+            out[cg * MEMS_WIDTH + nn] = tanhf(z0 + b);
+            out[(cg + ngrp) * MEMS_WIDTH + nn] = tanhf(z1 + b);
+            bar();
+            float* tmp = in; in = out; out = tmp;
+        }
+        if (t < CH * 16) {                                 // 64 -> 15, linear
+            const int c = t >> 4, o = t & 15;
+            float z = 0.0f;
+            if (o < MEMS_COARSE_OUT) {
+                for (int k = 0; k < MEMS_WIDTH; ++k) z = fmaf(in[c * MEMS_WIDTH + k], __ldg(&cm->Wo[k * 16 + o]), z);
+                z += __ldg(&cm->bo[o]);
+            }
+            out[c * MEMS_WIDTH + o] = z;
+        }
+        bar();
+        if (t < CH && base + t < n) {                      // band-limited misfit from the 15 features
+            const float* f = out + t * MEMS_WIDTH;
+            const double m = 0.1 * (double)f[0];
+            double dot = m * cm->sum_y, nrm = (double)T * m * m;
+            const double w2 = 2.0 / (double)T;
+            for (int k = 0; k < MEMS_COARSE_HARM; ++k) {
+                const double A = (double)f[1 + k], phi = 0.01 * (double)f[1 + MEMS_COARSE_HARM + k];
+                double sn, cs;
+                sincos(phi, &sn, &cs);
+                dot += w2 * A * (cs * cm->cy[k] - sn * cm->sy[k]);
+                nrm += w2 * A * A;
+            }
+            const int idx = map ? (int)map[base + t] : base + t;
+            S[idx] = cm->sum_y2 - 2.0 * dot + nrm;
+        }
+    }
+    bar();
+}
+
 __device__ __forceinline__ int batch_pass_stride(const MemsRunArgs& ra, int sub) {
     return (ra.mode == MEMS_MODE_DA && sub == 0) ? ra.da_stride : 1;
 }
@@ -353,11 +459,13 @@ __device__ __forceinline__ void batch_post(ChainBatch& cb, const MemsConsts& pb,
     } else {                                            // delayed acceptance
         if (sub == 0) {
             // coarse stage: S covers every da_stride-th time point; rescaled to the full trace length
-            const int Tc = (pb.T + ra.da_stride - 1) / ra.da_stride;
+            const int Tc = ra.coarse ? pb.T : (pb.T + ra.da_stride - 1) / ra.da_stride;
             const double llc_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S * ((double)pb.T / (double)Tc) : -CUDART_INF;
             const bool prom = mh_accept(cb.lu[0][j], llc_star, cb.llc[j]);
             cb.llc_star[j] = llc_star;
-            cb.live[j] = prom ? 1 : 0;
+            // 1: promoted and to be evaluated; 2: promoted by the min(0, nan) = 0 quirk although the proposal lies outside
+            // the prior box (state and proposal both at -inf) -- stage 2 decides without evaluating the surrogate
+            cb.live[j] = prom ? (cb.inb[j] ? 1 : 2) : 0;
             if (prom) cb.prom_count[j] += 1u;
             if (ra.xi != nullptr) {
                 if (ra.llprop_out) ra.llprop_out[orow] = llc_star;
@@ -367,7 +475,7 @@ __device__ __forceinline__ void batch_post(ChainBatch& cb, const MemsConsts& pb,
             bool acc = false;
             double ll_star = -CUDART_INF;
             if (cb.live[j]) {
-                ll_star = pb.neg_half_inv_sigma2 * S;
+                ll_star = cb.inb[j] ? pb.neg_half_inv_sigma2 * S : -CUDART_INF;
                 // [pi(x*) pi~(x)] / [pi(x) pi~(x*)]
                 acc = mh_accept(cb.lu[1][j], (ll_star - cb.ll[j]) - (cb.llc_star[j] - cb.llc[j]), 0.0);
             }
@@ -413,5 +521,6 @@ int mems_tc_choose_nc(int C, int T, int sm_count);
 int mems_fp32_choose_nc(int C, int T, int sm_count);
 int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st);
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);
+int mems_coarse_ll_launch(const MemsLaunchCtx& ctx, const MemsCoarse* cm_dev, const double* x_dev, int n, double* ll_out);
 int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned long long step0, int n_steps,
                      double* xi_out, double* log_u_out);

@@ -83,7 +83,7 @@ __device__ __forceinline__ void eval_batch(Fp32Smem& sm, const double* s_yobs, c
     const int tslot = tid / nc;
     const int nts = NT / nc;
     double Sp = 0.0;
-    if (j < ncv && tslot < nts && (!skip_dead || sm.cb.live[j])) {
+    if (j < ncv && tslot < nts && (!skip_dead || sm.cb.live[j] == 1)) {
         float xs[MEMS_PMAX];
         for (int p = 0; p < P; ++p) xs[p] = sm.cb.xs[p][j];
         float* a = sm.act + tid;
@@ -125,7 +125,11 @@ fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs 
             for (int sub = 0; sub < ra.n_sub; ++sub) {
                 if (tid < ncv) batch_pre(sm.cb, sm.c, ch, ra, c0, tid, s, sub);
                 __syncthreads();
-                eval_batch(sm, s_yobs, s_ts, P, T, batch_pass_stride(ra, sub), b7, nc, ncv, true, nullptr, c0);
+                if (batch_pass_is_coarse_model(ra, sub))       // DA first stage on the FFT surrogate: S_c for every chain
+                    coarse_fft_pass(ra.coarse, P, T, &sm.cb.xp[0][0], MEMS_NCMAX, nullptr, ncv, sm.Spart, sm.act, tid, NT,
+                                    [] { __syncthreads(); });
+                else
+                    eval_batch(sm, s_yobs, s_ts, P, T, batch_pass_stride(ra, sub), b7, nc, ncv, true, nullptr, c0);
                 if (tid < ncv) batch_post(sm.cb, sm.c, ch, ra, c0, tid, s, sub, sm.Spart[tid]);
                 __syncthreads();
             }
@@ -167,6 +171,30 @@ fp32_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restric
             const int Tn = (T + stride - 1) / stride;
             const double ll = sm.c.neg_half_inv_sigma2 * sm.Spart[tid] * ((double)T / (double)Tn);
             ll_out[c0 + tid] = (apply_prior && !sm.cb.inb[tid]) ? -CUDART_INF : ll;
+        }
+    }
+}
+
+// Coarse log-likelihood of arbitrary points (the DA start states): ll[i] = -0.5*S_c(x_i)/sigma2, -inf outside the box.
+__global__ void __launch_bounds__(NT)
+coarse_ll_kernel(const MemsProblem* __restrict__ pbp, const MemsCoarse* __restrict__ cm, const double* __restrict__ x, int n,
+                 double* __restrict__ ll_out) {
+    __shared__ double xs[MEMS_PMAX][MEMS_NCMAX];
+    __shared__ double S[MEMS_NCMAX];
+    __shared__ float act[2 * (2 * NT / 64) * MEMS_WIDTH];
+    const MemsConsts& c = pbp->c;
+    const int tid = threadIdx.x;
+    const int nbatch = (n + MEMS_NCMAX - 1) / MEMS_NCMAX;
+    for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+        const int c0 = batch * MEMS_NCMAX, ncv = min(MEMS_NCMAX, n - c0);
+        __syncthreads();
+        for (int i = tid; i < c.P * ncv; i += NT) xs[i / ncv][i % ncv] = x[(size_t)(i / ncv) * n + c0 + i % ncv];
+        __syncthreads();
+        coarse_fft_pass(cm, c.P, c.T, &xs[0][0], MEMS_NCMAX, nullptr, ncv, S, act, tid, NT, [] { __syncthreads(); });
+        if (tid < ncv) {
+            bool inb = true;
+            for (int p = 0; p < c.P; ++p) inb = inb && !(xs[p][tid] < c.low[p]) && !(xs[p][tid] > c.high[p]);
+            ll_out[c0 + tid] = inb ? c.neg_half_inv_sigma2 * S[tid] : -CUDART_INF;
         }
     }
 }
@@ -294,6 +322,14 @@ int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned lon
     if (grid > 8 * ctx.sm_count) grid = 8 * ctx.sm_count;
     if (grid < 1) grid = 1;
     draw_kernel<<<grid, 256, 0, ctx.stream>>>(ctx.pb_dev, ctx.chains, mode, n_sub, step0, n_steps, xi_out, log_u_out);
+    return (int)cudaGetLastError();
+}
+
+int mems_coarse_ll_launch(const MemsLaunchCtx& ctx, const MemsCoarse* cm_dev, const double* x_dev, int n, double* ll_out) {
+    int blocks = (n + MEMS_NCMAX - 1) / MEMS_NCMAX;
+    if (blocks > 4 * ctx.sm_count) blocks = 4 * ctx.sm_count;
+    if (blocks < 1) blocks = 1;
+    coarse_ll_kernel<<<blocks, NT, 0, ctx.stream>>>(ctx.pb_dev, cm_dev, x_dev, n, ll_out);
     return (int)cudaGetLastError();
 }
 

@@ -262,7 +262,7 @@ __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt,
 #pragma unroll
         for (int c = 0; c < MEMS_NCMAX / 32; ++c) {
             const int jj = 32 * c + gt;
-            const bool lv = jj < ncv && gs.cb.live[jj] != 0;
+            const bool lv = jj < ncv && gs.cb.live[jj] == 1;
             const unsigned m = __ballot_sync(0xffffffffu, lv);
             if (lv) gs.map[base + __popc(m & ((1u << gt) - 1u))] = (unsigned char)jj;
             base += __popc(m);
@@ -354,10 +354,13 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                     // proposals the DA first stage did not promote drop out); no live chain -> the pass is skipped
                     group_compact_live<NH>(gs, g, gt, ncv);
                     const bool any = gs.nlive > 0;
-                    if (any)
+                    if (any && batch_pass_is_coarse_model(ra, sub))   // DA first stage on the FFT surrogate (FP32, CUDA cores)
+                        coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, gs.cact, gt, GT,
+                                        [g] { group_bar_sync<NH>(g); });
+                    else if (any)
                         tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, ncv, true,
                                              nullptr, c0, phD);
-                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt]) ? gs.Sfin[gt] : 0.0);
+                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt] == 1) ? gs.Sfin[gt] : 0.0);
                 }
             }
             batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);

@@ -60,6 +60,7 @@ struct GroupSmem {
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
+    float cact[2 * 8 * MEMS_WIDTH];    // scratch of the coarse (FFT surrogate) first stage of delayed acceptance
 };
 
 struct TcSmem {

@@ -372,12 +372,23 @@ class DelayedAcceptanceMH(MH):
     (SURVEY.md F2); same constructor and return types as :class:`MH`."""
     _sampler = SAMPLER_DA
 
-    def __init__(self, *a, stride: int = 4, **k):
+    def __init__(self, *a, stride: int = 4, coarse_model=None, coarse_scaler=None, **k):
+        """``coarse_model`` / ``coarse_scaler``: the reference's FFT surrogate (``NN_Model`` loaded from
+        ``model_VoltageSignal_fft.keras``) and the scaler of its data processor (``preprocessing(config_I_fft).scaler``);
+        when given they replace the time-strided first stage (``stride`` is then ignored)."""
         super().__init__(*a, **k)
         self.stride = int(stride)
+        self.coarse_model, self.coarse_scaler = coarse_model, coarse_scaler
+        if (coarse_model is None) != (coarse_scaler is None):
+            raise ValueError("give both coarse_model and coarse_scaler or neither")
 
     def _configure(self, eng):
-        eng.set_sampler(SAMPLER_DA, da_stride=self.stride)
+        if self.coarse_model is not None:
+            net = getattr(self.coarse_model, "model", self.coarse_model)
+            eng.set_coarse_fft(net.layers, self.coarse_scaler.mean_, self.coarse_scaler.scale_)
+            eng.set_sampler(SAMPLER_DA, da_stride=0)
+        else:
+            eng.set_sampler(SAMPLER_DA, da_stride=self.stride)
 
 
 class CWMH(MH):

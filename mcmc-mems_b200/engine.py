@@ -202,11 +202,32 @@ class MHEngine:
                                     _stream(self.device)), "mems_lsq")
         return xo.t().contiguous(), cov, cost, its
 
+    # -- coarse first-stage model of delayed acceptance -----------------------------
+    def set_coarse_fft(self, layers, scaler_mean, scaler_scale):
+        """Install the reference's FFT surrogate ([P] -> 64x6 tanh -> 15 features) as the DA first stage
+        (``mems_set_coarse_fft``); select it with ``set_sampler(SAMPLER_DA, da_stride=0)``."""
+        shapes = [(self.P, 64)] + [(64, 64)] * 5 + [(64, 15)]
+        if len(layers) != 7:
+            raise ValueError(f"expected 7 Dense layers, got {len(layers)}")
+        for i, ((k, b, act), shp) in enumerate(zip(layers, shapes)):
+            if tuple(np.asarray(k).shape) != shp or tuple(np.asarray(b).shape) != (shp[1],):
+                raise ValueError(f"coarse layer {i}: kernel {np.asarray(k).shape} / bias {np.asarray(b).shape}, expected {shp}")
+            if act != ("linear" if i == 6 else "tanh"):
+                raise ValueError(f"coarse layer {i}: activation {act!r}")
+        Ws = [_host(k, np.float32) for k, _, _ in layers]
+        bs = [_host(b, np.float32) for _, b, _ in layers]
+        Wp = (C.c_void_p * 7)(*[w.ctypes.data for w in Ws])
+        bp = (C.c_void_p * 7)(*[b.ctypes.data for b in bs])
+        m, sc = _host(scaler_mean), _host(scaler_scale)
+        if m.shape != (self.P,) or sc.shape != (self.P,):
+            raise ValueError("coarse scaler constants must have P entries")
+        _lib.check(self._L.mems_set_coarse_fft(self._h, Wp, bp, m.ctypes.data, sc.ctypes.data), "mems_set_coarse_fft")
+
     # -- sampler variant ---------------------------------------------------------
     def set_sampler(self, sampler: int, cw_scale=None, da_stride: int = 4):
         """SAMPLER_MH (reference), SAMPLER_CWMH (component-wise; ``cw_scale[P]`` = initial per-component
-        proposal std) or SAMPLER_DA (delayed acceptance; coarse stage = every ``da_stride``-th time point).
-        Call before :meth:`init_chains`."""
+        proposal std) or SAMPLER_DA (delayed acceptance; coarse stage = every ``da_stride``-th time point, or the
+        FFT surrogate installed with :meth:`set_coarse_fft` when ``da_stride == 0``).  Call before :meth:`init_chains`."""
         cw = None if cw_scale is None else _host(np.broadcast_to(np.asarray(cw_scale, np.float64), (self.P,)))
         _lib.check(self._L.mems_set_sampler(self._h, int(sampler), None if cw is None else cw.ctypes.data,
                                             int(da_stride)), "mems_set_sampler")

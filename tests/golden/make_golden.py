@@ -126,11 +126,30 @@ def sensitivity():
              X_test_scaled=dp.X_test_scaled[:64], **pack_layers(layers))
 
 
+def fft_coarse():
+    """The FFT surrogate of the Q-factor test with the scaler of its own data processor (config_I_fft.json): the
+    coarse first-stage model of delayed acceptance (oracle/coarse.py)."""
+    tdir = os.path.join(REF, "tests", "Xaccelerometer_quality_factor")
+    cwd = os.getcwd()
+    os.chdir(tdir)
+    try:
+        dp = preprocessing("./config_I_fft.json")
+        layers = layers_of(dp.config["MODEL_PATH"])
+    finally:
+        os.chdir(cwd)
+    np.savez(os.path.join(HERE, "fft_coarse.npz"), scaler_mean=dp.scaler.mean_, scaler_scale=dp.scaler.scale_,
+             X_test=dp.X_test[:16], y_test=dp.y_test[:16], y_series_test=dp.y_series_test[:16], **pack_layers(layers))
+
+
 def main():
     if "--sensitivity-only" in sys.argv:
         sensitivity()
         return
+    if "--fft-coarse-only" in sys.argv:
+        fft_coarse()
+        return
     sensitivity()
+    fft_coarse()
     geo_bounds = ([0.1, -0.5, 29.0], [0.5, 0.5, 31.0])          # geometric cell 6
     geo_starts = [[0.3, 0.0, 30.0], [0.4, 0.25, 30.0], [0.2, 0.25, 30.0],
                   [0.4, -0.25, 30.0], [0.2, -0.25, 30.0]]

@@ -599,3 +599,57 @@ def test_sensitivity_push_forward_matches_oracle():
     assert out["ci_lower"] < out["mean"] < out["ci_upper"]
     batched = sensitivity_push_forward(np.stack([sample, sample]), net, dp.scaler)      # (C, P, Ns)
     assert batched["values"].shape == (2000,) and batched["mean"] == pytest.approx(out["mean"], rel=1e-6)
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_delayed_acceptance_with_fft_coarse_surrogate(path):
+    """DA whose first stage is the reference's FFT surrogate + reconstruction (oracle/coarse.py): start-state coarse
+    log-likelihoods and every two-stage decision replayed by the oracle (Q-factor problem, P = 4)."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("qfactor")
+    cf = helpers.fft_coarse()
+    coarse = helpers.coarse_ll_fn(pb, cf)
+    C, S = 44, 12
+    x0, xi, _ = _explicit_inputs(pb, C, S, 19, spread=0.3)      # wide: some chains start outside the prior box (-inf)
+    log_u = np.log(np.random.default_rng(20).random((S, C, 2)))
+    eng = helpers.engine(pb, C, path)
+    eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+    eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+    eng.init_chains(x0, scale0=0.3)
+    want0 = coarse(x0)
+    got0 = eng.aux_state()["loglik_coarse"].cpu().numpy()
+    assert np.array_equal(np.isfinite(got0), np.isfinite(want0))
+    fin = np.isfinite(want0)
+    assert np.allclose(got0[fin], want0[fin], rtol=1e-4, atol=1e-3)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
+    res = helpers.check_explicit_da(pb, x0, 0.3, 0, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy(),
+                                    BAND[path], coarse_ll=coarse)
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert 0 < res["accepted"] <= res["promoted"] < C * S
+    eng.close()
+
+
+def test_fft_coarse_delayed_acceptance_preserves_the_posterior():
+    """Christen-Fox invariance with the FFT coarse stage: same posterior moments as plain MH (Q-factor problem)."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("qfactor")
+    cf = helpers.fft_coarse()
+    C, N = 512, 3000
+    x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
+    out = {}
+    for name in ("mh", "da"):
+        eng = helpers.engine(pb, C, 1)
+        if name == "da":
+            eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+            eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+        eng.init_chains(x0, scale0=0.218, seed=78)
+        eng.run(1000, 0, 1, keep_samples=False)
+        smp, _ = eng.run(N, 0, 10)
+        S = smp.cpu().numpy().transpose(1, 0, 2).reshape(4, -1)
+        rate = eng.state()["accept_count"].double().mean().item() / (N + 1000)
+        prom = eng.aux_state()["promote_count"].double().mean().item() / (N + 1000) if name == "da" else 1.0
+        out[name] = (S.mean(axis=1), S.std(axis=1), rate, prom)
+        eng.close()
+    assert np.all(np.abs(out["da"][0] - out["mh"][0]) < 0.1 * out["mh"][1]), out
+    assert np.all(np.abs(out["da"][1] / out["mh"][1] - 1) < 0.1), out
+    assert out["da"][2] <= out["mh"][2] + 0.01 and out["da"][3] < 0.95

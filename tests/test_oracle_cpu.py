@@ -158,3 +158,35 @@ def test_preprocessing_mirror_reproduces_reference_constants(tmp_path):
     assert np.allclose(dp.scaler.scale_, g["scaler_scale"], rtol=1e-14)
     assert np.array_equal(dp.X_test[10], g["x_true"]) and np.array_equal(dp.y_test[10], g["y_true"])
     assert dp.X_train_scaled.shape == (640 * 150, 4)
+
+
+def test_fft_coarse_reconstruction_follows_the_notebook():
+    """oracle/coarse.py: the reconstruction of surrogate_fft.ipynb cell 15 equals the closed-form cosine sum, and the
+    squared misfit equals its orthogonal-projection form (what the device evaluates)."""
+    from oracle.coarse import features_to_trace, batched_coarse_forward, coarse_loglik
+    cf = helpers.fft_coarse()
+    T = 150
+    # the true features of a series reproduce the series up to its content above the 7th harmonic
+    rec = features_to_trace(cf["y_test"], T)
+    assert np.sqrt(np.mean((rec - cf["y_series_test"]) ** 2)) < 0.02 * cf["y_series_test"].std()
+    t = np.arange(T)
+    pred = cf["y_test"][3]
+    closed = 0.1 * pred[0] + (2.0 / T) * sum(pred[k] * np.cos(2 * np.pi * k * t / T + 0.01 * pred[7 + k]) for k in range(1, 8))
+    assert np.allclose(rec[3], closed, rtol=0, atol=1e-10)
+    # surrogate + reconstruction tracks the held-out series to a few noise standard deviations (sigma = 0.71)
+    c = batched_coarse_forward(cf["layers"], cf["scaler_mean"], cf["scaler_scale"], cf["X_test"], T)
+    assert np.sqrt(np.mean((c - cf["y_series_test"]) ** 2)) < 2.5
+    # ||y - y_c||^2 = sum y^2 - 2 <y, y_c> + ||y_c||^2 with 16 projections of y
+    pb = helpers.load_problem("qfactor")
+    y = pb["y_obs"]
+    X = cf["X_test"][:5]
+    ll = coarse_loglik(cf["layers"], cf["scaler_mean"], cf["scaler_scale"], X, y, pb["sigma2"], pb["low"], pb["high"])
+    from oracle.surrogate import mlp_forward
+    f = mlp_forward(cf["layers"], ((X - cf["scaler_mean"]) / cf["scaler_scale"]).astype(np.float32)).astype(np.float64)
+    m, A, ph = 0.1 * f[:, 0], f[:, 1:8], 0.01 * f[:, 8:15]
+    k = np.arange(1, 8)
+    cy = (y[None, :] * np.cos(2 * np.pi * k[:, None] * t[None, :] / T)).sum(axis=1)
+    sy = (y[None, :] * np.sin(2 * np.pi * k[:, None] * t[None, :] / T)).sum(axis=1)
+    dot = m * y.sum() + (2.0 / T) * np.sum(A * (np.cos(ph) * cy - np.sin(ph) * sy), axis=1)
+    nrm = T * m * m + (2.0 / T) * np.sum(A * A, axis=1)
+    assert np.allclose(-0.5 * (np.sum(y * y) - 2 * dot + nrm) / pb["sigma2"], ll, rtol=1e-10)

@@ -37,3 +37,26 @@ for name, sampler, kw, scale0 in (("mh", E.SAMPLER_MH, {}, 0.128), ("da stride 4
         extra = f", promoted {eng.aux_state()['promote_count'].double().mean().item() / (steps + 20):.3f}"
     print(f"{name:12s} {C} chains: {C * steps / dt / 1e6:8.2f} M chain-steps/s, acceptance {acc:.3f}{extra}")
     eng.close()
+
+# Q-factor problem (P = 4, sigma2 = 0.5): plain MH, strided DA and DA with the reference's FFT surrogate as first stage
+pbq = helpers.load_problem("qfactor")
+cf = helpers.fft_coarse()
+x0q = np.tile(pbq["x_opts"], (C // 5 + 1, 1))[:C]
+for name, setup in (("qf mh", None), ("qf da stride 4", "stride"), ("qf da fft", "fft")):
+    eng = helpers.engine(pbq, C, 1)
+    if setup == "stride":
+        eng.set_sampler(E.SAMPLER_DA, da_stride=4)
+    elif setup == "fft":
+        eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+        eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+    eng.init_chains(x0q, scale0=0.218, seed=3)
+    eng.run(20, 0, 1, keep_samples=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.run(steps, 0, 1, keep_samples=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    acc = eng.state()["accept_count"].double().mean().item() / (steps + 20)
+    extra = f", promoted {eng.aux_state()['promote_count'].double().mean().item() / (steps + 20):.3f}" if setup else ""
+    print(f"{name:14s} {C} chains: {C * steps / dt / 1e6:8.2f} M chain-steps/s, acceptance {acc:.3f}{extra}")
+    eng.close()
