@@ -300,6 +300,7 @@ def run_ours(args):
     post, _ = eng.run(800, 0, 8)
     rhat = D.split_rhat(post)
     mean, std = D.posterior_moments(post)
+    ess, _ = D.ess(post, max_lag=post.shape[0])          # device autocovariance sums + one all-reduce
     acc_rate = float(acc_host.double().mean().item() / S)
 
     if rank == 0:
@@ -332,7 +333,8 @@ def run_ours(args):
             "clocks": clk,
             "wall_s_timed_region": wall,
             "check": {"split_rhat": [float(v) for v in rhat.cpu()], "post_mean": [float(v) for v in mean.cpu()],
-                      "post_std": [float(v) for v in std.cpu()], "accept_rate_last_step": acc_rate},
+                      "post_std": [float(v) for v in std.cpu()], "accept_rate_last_step": acc_rate,
+                      "ess_thinned_draws": [float(v) for v in ess], "kept_draws": int(post.shape[0] * post.shape[2] * world)},
         }
         if cpu_rate is not None:
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
