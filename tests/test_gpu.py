@@ -581,6 +581,20 @@ def test_batched_least_squares_many_observations_and_bounds():
     eng.close()
 
 
+def test_batched_least_squares_reference_shaped_call():
+    """utils.batched_least_squares: the notebook's five least_squares_optimization calls as one call."""
+    from mcmc_mems_b200 import FixtureProcessor, NN_Model, create_forward_model_function, batched_least_squares
+    pb = helpers.load_problem("geometric")
+    net = NN_Model()
+    net.set_layers(pb["layers"])
+    fwd = create_forward_model_function(FixtureProcessor(pb["time"], pb["scaler_mean"], pb["scaler_scale"]), net)
+    x, cov = batched_least_squares(pb["y_obs"], fwd, pb["starts"], (pb["low"], pb["high"]), rel_step=3e-4)
+    assert x.shape == (5, 3) and cov.shape == (5, 3, 3)
+    post_std = np.sqrt(np.diag(pb["cov"] * pb["sigma2"]))
+    assert np.all(np.abs(x - pb["x_opts"].mean(axis=0)) < np.ptp(pb["x_opts"], axis=0) + 0.5 * post_std)
+    assert np.all(np.linalg.eigvalsh(cov) > 0)
+
+
 def test_sensitivity_push_forward_matches_oracle():
     import os
     from mcmc_mems_b200 import NN_Model, FixtureProcessor, sensitivity_push_forward
