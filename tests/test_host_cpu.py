@@ -169,3 +169,16 @@ def test_sensitivity_fixture_and_push_forward_math():
     pred = mlp_forward(layers, rows.astype(np.float32)).reshape(-1)
     rel = np.abs(pred - d["y_test"]) / np.abs(d["y_test"])
     assert np.median(rel) < 0.01 and rel.max() < 0.05
+
+
+def test_bench_reference_arm_pieces_run_on_cpu():
+    """bench.py --impl reference times this function on every host core: keep it importable and sane without a GPU."""
+    import bench
+    dt = bench._cpu_chain(("geometric", 150, 40, 0))
+    assert 0.0 < dt < 30.0
+    assert bench.flop_per_row(3) == 41600 and bench.flop_per_row(4) == 41728
+    class A:   # noqa: E701
+        workload, chains, inner, thin, path = "geometric_4096", 4096, 256, 64, "tc"
+    assert bench.measured_traffic(A) > 100000
+    A.chains = 1024
+    assert bench.measured_traffic(A) is None
