@@ -120,7 +120,11 @@ __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, gt
 // compact: only the gs.nlive chains listed in gs.map take part (nce = gs.nlive): proposals outside the prior box and,
 // in the delayed-acceptance second stage, proposals the first stage did not promote cost nothing -- the tiles are
 // rebuilt from the live chains, so the pass shrinks with the promotion rate.  Result: gs.Sfin[chain].
-template <int P, int NH>
+// DENSE (compact passes only): (time, chain) pairs are laid out back to back, row i of tile k is pair f = 128k + i
+// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A thread
+// then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2) and
+// thread c < n_live adds the entries of chain slot c in time order (deterministic).
+template <int P, int NH, bool DENSE>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
                                               bool compact, float* y_out, int c0, uint32_t& phD) {
@@ -135,7 +139,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const int tpt = 128 / nce;                        // time points per tile
     const int j = compact ? (int)gs.map[jc] : jc;     // batch-local chain index
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
-    const int n_tiles = (Tn + tpt - 1) / tpt;
+    const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
     const bool chain_live = (sub < tpt) && (compact || jc < ncv);
@@ -148,23 +152,37 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     if (h == 0) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
+        if (!DENSE) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
+            for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
+        }
         set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
         set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
         set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
     }
+    // layer-1 operand of `tile` into slot s (column-half 0 threads)
+    auto stage_tile = [&](int s, int tile) {
+        if (DENSE) {
+            const int f = tile * 128 + row;
+            const int ti = f / nce;
+            const bool ok = ti < Tn;
+            const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
+            put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
+        } else {
+            const int ti = tile * tpt + sub;
+            put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
+        }
+        tmem_st16(tD0 + s * 128 + 64, a1);
+        tc_wait_st();
+    };
 
     // prologue: layer-1 operands of the first tile of each slot
 #pragma unroll
     for (int s = 0; s < GSLOT; ++s) {
         if (s < n_tiles) {
-            if (h == 0) {
-                const int ti = s * tpt + sub;
-                put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
-                tmem_st16(tD0 + s * 128 + 64, a1);
-                tc_wait_st();
-            }
+            if (h == 0) stage_tile(s, s);
             tc_fence_before();
             mbar_arrive(&gs.bar_A[s]);
         }
@@ -216,23 +234,35 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         }
                         if (h == 0) {
                             o += sm.b7;
-                            const int ti = tile * tpt + sub;
-                            const int t = ti * stride;
-                            if (chain_live && ti < Tn) {
-                                if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
-                                const double r = s_yobs[t] - (double)o;
-                                Sp = fma(r, r, Sp);
+                            if (DENSE) {
+                                const int f = tile * 128 + row;
+                                const int ti = f / nce;
+                                double r2 = 0.0;
+                                if (ti < Tn) {
+                                    const double r = s_yobs[ti * stride] - (double)o;
+                                    r2 = r * r;
+                                }
+                                gs.R2[s][row] = r2;
+                                named_bar_sync(3 + g, 128);            // the tile's 128 residuals are in shared memory
+                                if (gt < nce) {                        // chain slot gt: its rows of this tile, in time order
+                                    int r0 = gt - (tile * 128) % nce;
+                                    if (r0 < 0) r0 += nce;
+                                    for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
+                                }
+                            } else {
+                                const int ti = tile * tpt + sub;
+                                const int t = ti * stride;
+                                if (chain_live && ti < Tn) {
+                                    if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                                    const double r = s_yobs[t] - (double)o;
+                                    Sp = fma(r, r, Sp);
+                                }
                             }
                         }
                         // this slot's D and A are free again: stage the layer-1 operand of its next tile
                         const int nt = tile + GSLOT;
                         if (nt < n_tiles) {
-                            if (h == 0) {
-                                const int ti2 = nt * tpt + sub;
-                                put_input<P>(a1, P, s_ts[(ti2 < Tn && sub < tpt) ? ti2 * stride : 0]);
-                                tmem_st16(tD + 64, a1);
-                                tc_wait_st();
-                            }
+                            if (h == 0) stage_tile(s, nt);
                             tc_fence_before();
                             mbar_arrive(&gs.bar_A[s]);
                         } else {
@@ -243,12 +273,16 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             }
         }
     }
-    if (h == 0) gs.Spart[row] = Sp;
-    group_bar_sync<NH>(g);
-    if (gt < nce) {
-        double S = 0.0;                                // fixed order: time sub-rows ascending
-        for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
-        gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
+    if (DENSE) {
+        if (gt < nce) gs.Sfin[gs.map[gt]] = Sp;        // thread gt summed chain slot gt over all tiles
+    } else {
+        if (h == 0) gs.Spart[row] = Sp;
+        group_bar_sync<NH>(g);
+        if (gt < nce) {
+            double S = 0.0;                            // fixed order: time sub-rows ascending
+            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
+            gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
+        }
     }
     group_bar_sync<NH>(g);                             // Sfin[chain] may have been written by another thread
 }
@@ -357,9 +391,15 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                     if (any && batch_pass_is_coarse_model(ra, sub))   // DA first stage on the FFT surrogate (FP32, CUDA cores)
                         coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, gs.cact, gt, GT,
                                         [g] { group_bar_sync<NH>(g); });
-                    else if (any)
-                        tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, batch_pass_stride(ra, sub), nc, ncv, true,
-                                             nullptr, c0, phD);
+                    else if (any) {
+                        // dense packing when it saves tiles (n_live does not divide 128 well)
+                        const int stride = batch_pass_stride(ra, sub);
+                        const int Tn = (T + stride - 1) / stride, tpt = 128 / gs.nlive;
+                        if ((gs.nlive * Tn + 127) / 128 < (Tn + tpt - 1) / tpt)
+                            tc_eval_group<P, NH, true>(sm, gs, g, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, phD);
+                        else
+                            tc_eval_group<P, NH, false>(sm, gs, g, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, phD);
+                    }
                     if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt] == 1) ? gs.Sfin[gt] : 0.0);
                 }
             }
@@ -414,7 +454,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
                 gs.cb.live[gt] = 1;
             }
             group_bar_sync<NH>(g);
-            tc_eval_group<P, NH>(sm, gs, g, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, phD);
+            tc_eval_group<P, NH, false>(sm, gs, g, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, phD);
             if (gt < ncv && ll_out) {
                 // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
                 const int Tn = (T + stride - 1) / stride;

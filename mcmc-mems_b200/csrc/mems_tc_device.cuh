@@ -61,6 +61,7 @@ struct GroupSmem {
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
     float cact[2 * 8 * MEMS_WIDTH];    // scratch of the coarse (FFT surrogate) first stage of delayed acceptance
+    double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
 };
 
 struct TcSmem {
