@@ -140,6 +140,12 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10)
         return fail(MEMS_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    {   // the observation and the time column live in shared memory next to the resident weights
+        const int tmax = (cfg->path == MEMS_PATH_TC) ? mems_tc_max_time_points(prop.sharedMemPerBlockOptin)
+                                                     : mems_fp32_max_time_points(prop.sharedMemPerBlockOptin);
+        if (cfg->n_time > tmax)
+            return fail(MEMS_E_INVALID, "n_time=%d does not fit in shared memory on this path (max %d)", cfg->n_time, tmax);
+    }
     CUDA_TRY(cudaSetDevice(cfg->device));
     MemsHandle_* h = new (std::nothrow) MemsHandle_();
     if (!h) return fail(MEMS_E_INVALID, "out of host memory");

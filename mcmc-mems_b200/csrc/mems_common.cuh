@@ -518,6 +518,8 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
                     int apply_prior, int t_stride);
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra);
 int mems_tc_choose_nc(int C, int T, int sm_count);
+int mems_tc_max_time_points(size_t smem_optin);
+int mems_fp32_max_time_points(size_t smem_optin);
 int mems_fp32_choose_nc(int C, int T, int sm_count);
 int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st);
 int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);

@@ -277,6 +277,12 @@ size_t fp32_smem_bytes(int T) { return sizeof(Fp32Smem) + (size_t)T * (sizeof(do
 
 }  // namespace
 
+int mems_fp32_max_time_points(size_t smem_optin) {
+    const size_t fixed = fp32_smem_bytes(0);
+    if (smem_optin <= fixed) return 0;
+    return (int)((smem_optin - fixed) / (sizeof(double) + sizeof(float)));
+}
+
 // Chains per block batch (any value 1..128): minimise (waves of batches) x (time points per thread).
 int mems_fp32_choose_nc(int C, int T, int sm_count) {
     int best = 1;

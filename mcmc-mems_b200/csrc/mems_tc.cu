@@ -624,6 +624,13 @@ int tc_nh() {
 
 size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
 
+// largest trace length whose observation / time columns fit next to the resident weights in `smem_optin` bytes
+int mems_tc_max_time_points(size_t smem_optin) {
+    const size_t fixed = tc_smem_bytes(0);
+    if (smem_optin <= fixed) return 0;
+    return (int)((smem_optin - fixed) / (sizeof(double) + sizeof(float)));
+}
+
 // Chains per group batch (any value 1..128): minimise (waves of batches over the 2*SMs groups) x (tile pairs per step).
 int mems_tc_choose_nc(int C, int T, int sm_count) {
     int best = 1;
