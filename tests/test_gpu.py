@@ -484,6 +484,18 @@ def test_cuqi_cwmh_and_da_lookalikes():
     assert d.samples.shape == (3, 800) and 0.0 < d.acc_rate < 0.5
 
 
+def test_trace_length_limit_is_reported_at_creation():
+    """y_obs and the time column live in shared memory: a trace that does not fit is refused with the limit in the message."""
+    from mcmc_mems_b200 import MemsError
+    pb = helpers.load_problem("geometric")
+    pb["time"] = np.linspace(0.0, 1.49e-3, 2000)
+    pb["y_obs"] = np.zeros(2000)
+    with pytest.raises(MemsError, match="does not fit in shared memory"):
+        helpers.engine(pb, 4, 1)
+    eng = helpers.engine(pb, 4, 0)          # the FP32 check path holds up to 3621 points
+    eng.close()
+
+
 # ----------------------------------------------------------------------------- rows either side of the path (SURVEY 8f)
 def test_autocov_kernel_and_device_ess():
     from mcmc_mems_b200 import diagnostics as D, distributed
