@@ -32,6 +32,25 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "surrogate-scored chain-steps/sec"
 UNIT = "chain-steps/s"
 
+# The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 behind Python's back (NCCL
+# prints its version there when /etc/nccl.conf or the environment asks for it), so fd 1 is pointed at stderr for the
+# whole run and the JSON line goes to a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 
 def flop_per_row(P):
     return 2 * ((P + 1) * 64 + 5 * 64 * 64 + 64)
@@ -177,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, P, cores_note=None):
@@ -209,8 +228,7 @@ def run_ours(args):
         g.build()
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")    # an explicit setting wins over /etc/nccl.conf
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local}"))
         dist.barrier()
     g.build()
@@ -340,7 +358,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"1 chain x {cpu_n} MH updates, numpy restatement of utils.py:30-40 + "
                                               "CUQIpy 0.8.0 MH on one host core (TF/CUQIpy not installable here)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     eng.close()
     if world > 1:
         dist.barrier()
@@ -364,6 +382,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    _protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
