@@ -484,6 +484,53 @@ def test_cuqi_cwmh_and_da_lookalikes():
     assert d.samples.shape == (3, 800) and 0.0 < d.acc_rate < 0.5
 
 
+def _synthetic_problem(P, T=40, seed=0):
+    """Shape-only problem of SURVEY 8d: Glorot-uniform weights (default_rng(0)), scaler from the box, synthetic trace."""
+    from oracle import batched_forward
+    rng = np.random.default_rng(seed)
+    shapes = [(P + 1, 64)] + [(64, 64)] * 5 + [(64, 1)]
+    layers = []
+    for i, (fi, fo) in enumerate(shapes):
+        lim = np.sqrt(6.0 / (fi + fo))
+        layers.append((rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32),
+                       (0.1 * rng.standard_normal(fo)).astype(np.float32), "linear" if i == 6 else "tanh"))
+    low, high = -np.ones(P), np.ones(P)
+    time = np.linspace(0.0, 1.0, T)
+    mean = np.concatenate([(low + high) / 2, [time.mean()]])
+    scale = np.concatenate([(high - low) / np.sqrt(12.0), [time.std()]])
+    x_true = rng.uniform(-0.5, 0.5, P)
+    sigma2 = 1e-4
+    f = batched_forward(time, mean, scale, layers, x_true[None])[0]
+    y_obs = f + np.sqrt(sigma2) * rng.standard_normal(T)
+    return {"layers": layers, "time": time, "scaler_mean": mean, "scaler_scale": scale, "low": low, "high": high,
+            "sigma2": sigma2, "y_obs": y_obs, "x_true": x_true, "cov": 1e-4 * np.eye(P), "x_opts": x_true[None, :]}
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("P", [1, 2])
+def test_one_and_two_parameter_surrogates(P, path):
+    """The kernels are instantiated for P = 1..4; the reference ships P = 3 and 4 only, so P = 1, 2 run on the
+    shape-only synthetic problem: forward parity and an explicit-randomness MH run against the oracle."""
+    from oracle import batched_forward
+    pb = _synthetic_problem(P)
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-1.0, 1.0, size=(150, P))
+    eng = helpers.engine(pb, 1, path)
+    y, ll = eng.forward(X)
+    want = batched_forward(pb["time"], pb["scaler_mean"], pb["scaler_scale"], pb["layers"], X, np.float64)
+    assert _out_rel(y.cpu().numpy(), want) < OUT_RTOL[path]
+    eng.close()
+    C, S = 33, 16
+    x0, xi, log_u = _explicit_inputs(pb, C, S, 6, spread=1.0)
+    eng = helpers.engine(pb, C, path)
+    eng.init_chains(x0, scale0=0.5)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u)
+    res = helpers.check_explicit_run(pb, x0, 0.5, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy(), band=BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert 0 < dec.sum().item() < C * S
+    eng.close()
+
+
 def test_trace_length_limit_is_reported_at_creation():
     """y_obs and the time column live in shared memory: a trace that does not fit is refused with the limit in the message."""
     from mcmc_mems_b200 import MemsError
