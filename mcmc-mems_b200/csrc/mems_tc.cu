@@ -611,15 +611,6 @@ int launch_by_p(int Pv, K1 k1, K2 k2, K3 k3, K4 k4, int grid, size_t smem, cudaS
     }
 }
 
-int g_tc_variant = -1;   // -1: read MEMS_TC_NH from the environment once
-int tc_nh() {
-    if (g_tc_variant < 0) {
-        const char* e = getenv("MEMS_TC_NH");
-        g_tc_variant = (e && e[0] == '1') ? 1 : 2;
-    }
-    return g_tc_variant;
-}
-
 }  // namespace
 
 size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
@@ -701,9 +692,6 @@ int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
     const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
     const int want = (nbatch + NGROUP - 1) / NGROUP;
     const int grid = want < ctx.sm_count ? want : ctx.sm_count;
-    if (tc_nh() == 1)
-        return launch_by_p<1>(ctx.pb_host->c.P, tc_run_kernel<1, 1>, tc_run_kernel<2, 1>, tc_run_kernel<3, 1>, tc_run_kernel<4, 1>,
-                              grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
     return launch_by_p<2>(ctx.pb_host->c.P, tc_run_kernel<1, 2>, tc_run_kernel<2, 2>, tc_run_kernel<3, 2>, tc_run_kernel<4, 2>,
                           grid, smem, ctx.stream, ctx.pb_dev, ctx.chains, ra);
 }
@@ -717,9 +705,6 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
     const int want = (nbatch + NGROUP - 1) / NGROUP;
     const int grid = want < ctx.sm_count ? want : ctx.sm_count;
     const int gr = grid > 0 ? grid : 1;
-    if (tc_nh() == 1)
-        return launch_by_p<1>(ctx.pb_host->c.P, tc_forward_kernel<1, 1>, tc_forward_kernel<2, 1>, tc_forward_kernel<3, 1>,
-                              tc_forward_kernel<4, 1>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
     return launch_by_p<2>(ctx.pb_host->c.P, tc_forward_kernel<1, 2>, tc_forward_kernel<2, 2>, tc_forward_kernel<3, 2>,
                           tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
 }
