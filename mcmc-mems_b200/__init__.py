@@ -11,11 +11,11 @@ from .utils import (create_forward_model_function, least_squares_optimization,  
                     objective_function, surrogate_spec, batched_least_squares, sensitivity_push_forward)
 from .cuqi_compat import (Gaussian, Uniform, JointDistribution, Posterior, Model, MH, CWMH,  # noqa: F401
                           DelayedAcceptanceMH, Samples, BatchedSamples, Continuous1D, Discrete)
-from . import diagnostics, distributed, h5lite  # noqa: F401
+from . import diagnostics, diagnostics_device, distributed, h5lite  # noqa: F401
 
 __all__ = [
     "MHEngine", "SurrogateSpec", "NN_Model", "preprocessing", "FixtureProcessor",
     "create_forward_model_function", "least_squares_optimization", "batched_least_squares", "sensitivity_push_forward", "Gaussian", "Uniform",
     "JointDistribution", "Posterior", "Model", "MH", "CWMH", "DelayedAcceptanceMH", "Samples", "BatchedSamples", "Continuous1D",
-    "Discrete", "diagnostics", "h5lite", "mlp_forward", "MemsError", "PATH_FP32", "PATH_TC",
+    "Discrete", "diagnostics", "diagnostics_device", "h5lite", "mlp_forward", "MemsError", "PATH_FP32", "PATH_TC",
 ]

@@ -245,24 +245,30 @@ class BatchedSamples:
     def std(self):
         return self.samples.transpose(1, 0, 2).reshape(self.samples.shape[1], -1).std(axis=1)
 
-    def compute_rhat(self):
-        return np.array([diagnostics.rhat_rank(self.samples[:, j, :]) for j in range(self.samples.shape[1])])
+    def _device_samples(self, device):
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(self.samples.transpose(2, 1, 0))).to(f"cuda:{device}")   # [Ns, P, C]
 
     def compute_ess(self, on_device: Optional[bool] = None, device: int = 0):
-        """Effective sample size per parameter over all chains.  Small batches follow arviz's default (rank-normalised
-        bulk ESS, host); large ones (or ``on_device=True``) use the classic multi-chain estimator with the
-        autocovariance sums computed on the GPU (``mems_chain_autocov``) -- shipping 10^6 chains to arviz is the
-        bottleneck the device path removes."""
+        """Bulk effective sample size per parameter over all chains (arviz's default, rank-normalised).  Large batches
+        (or ``on_device=True``) are ranked and reduced on the GPU (``diagnostics_device.ess_bulk``): shipping 10^6
+        chains to arviz is the bottleneck the device path removes."""
         C, P, Ns = self.samples.shape
         if on_device is None:
             on_device = C * Ns > 2_000_000
         if not on_device:
             return np.array([diagnostics.ess_bulk(self.samples[:, j, :]) for j in range(P)])
-        import torch
-        from . import distributed
-        smp = torch.as_tensor(np.ascontiguousarray(self.samples.transpose(2, 1, 0))).to(f"cuda:{device}")   # [Ns, P, C]
-        ess, _ = distributed.ess(smp, max_lag=min(Ns, 1024))
-        return ess
+        from . import diagnostics_device
+        return diagnostics_device.ess_bulk(self._device_samples(device))
+
+    def compute_rhat(self, on_device: Optional[bool] = None, device: int = 0):
+        C, P, Ns = self.samples.shape
+        if on_device is None:
+            on_device = C * Ns > 2_000_000
+        if not on_device:
+            return np.array([diagnostics.rhat_rank(self.samples[:, j, :]) for j in range(P)])
+        from . import diagnostics_device
+        return diagnostics_device.rhat_rank(self._device_samples(device))
 
 
 # -- sampler ---------------------------------------------------------------------------------

@@ -726,3 +726,31 @@ def test_fft_coarse_delayed_acceptance_preserves_the_posterior():
     assert np.all(np.abs(out["da"][0] - out["mh"][0]) < 0.1 * out["mh"][1]), out
     assert np.all(np.abs(out["da"][1] / out["mh"][1] - 1) < 0.1), out
     assert out["da"][2] <= out["mh"][2] + 0.01 and out["da"][3] < 0.95
+
+
+def test_rank_normalised_diagnostics_on_device_match_the_host_estimators():
+    """diagnostics_device (sort + ndtri + autocovariance kernel) against diagnostics.ess_bulk / rhat_rank (arviz
+    semantics), on chains with many ties (a Metropolis chain repeats its state at every rejection)."""
+    from mcmc_mems_b200 import diagnostics as D, diagnostics_device as DD
+    rng = np.random.default_rng(17)
+    n, P, Cn = 400, 3, 23
+    x = np.zeros((n, P, Cn))
+    cur = rng.standard_normal((P, Cn))
+    for k in range(n):                                    # random-walk MH on N(0,1): ~45 % rejections -> exact ties
+        prop = cur + 1.5 * rng.standard_normal((P, Cn))
+        acc = np.log(rng.random((P, Cn))) < 0.5 * (cur ** 2 - prop ** 2)
+        cur = np.where(acc, prop, cur)
+        x[k] = cur
+    x[:, 2, :] += np.linspace(0.0, 1.0, Cn)               # chains disagree on parameter 2
+    smp = torch.as_tensor(x, device="cuda")
+    ess = DD.ess_bulk(smp)
+    rhat = DD.rhat_rank(smp)
+    for p in range(P):
+        chains = x[:, p, :].T
+        assert ess[p] == pytest.approx(D.ess_bulk(chains), rel=1e-7)
+        assert rhat[p] == pytest.approx(D.rhat_rank(chains), rel=1e-9)
+    assert rhat[2] > rhat[0] and rhat[2] > 1.05
+    from mcmc_mems_b200 import BatchedSamples
+    b = BatchedSamples(x.transpose(2, 1, 0), None, np.zeros(Cn), np.ones(Cn))
+    assert np.allclose(b.compute_ess(on_device=True), b.compute_ess(on_device=False), rtol=1e-7)
+    assert np.allclose(b.compute_rhat(on_device=True), b.compute_rhat(on_device=False), rtol=1e-9)
