@@ -183,13 +183,14 @@ def test_explicit_run_parity(name, C, cpb, path):
 
 
 @pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
-def test_out_of_box_proposals_and_starts(path):
+@pytest.mark.parametrize("cpb", [0, 32], ids=["auto", "one_batch"])   # one batch: live-chain compaction + dense packing
+def test_out_of_box_proposals_and_starts(path, cpb):
     pb = helpers.load_problem("geometric")
     C, S = 32, 6
     x0, xi, log_u = _explicit_inputs(pb, C, S, 4)
     x0[:8, 0] = 0.7                                      # start outside the prior box: logd = -inf
     xi[0, 8:16, 2] = 1e3                                 # proposals far outside: always rejected
-    eng = helpers.engine(pb, C, path)
+    eng = helpers.engine(pb, C, path, chains_per_block=cpb)
     eng.init_chains(x0, scale0=0.1)
     assert np.all(np.isneginf(eng.state()["loglik"].cpu().numpy()[:8]))
     smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u)
@@ -377,7 +378,8 @@ def test_reference_shaped_api_end_to_end():
 
 # ----------------------------------------------------------------------------- sampler variants (unpinned in the reference)
 @pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
-def test_componentwise_mh_matches_oracle_semantics(path):
+@pytest.mark.parametrize("cpb", [0, 40], ids=["auto", "one_batch"])
+def test_componentwise_mh_matches_oracle_semantics(path, cpb):
     """CWMH (cuqi.sampler.CWMH semantics): P surrogate passes per update."""
     from mcmc_mems_b200 import engine as E
     pb = helpers.load_problem("geometric")
@@ -387,7 +389,7 @@ def test_componentwise_mh_matches_oracle_semantics(path):
     x0 = pb["x_opts"][0][None, :] + 0.3 * rng.standard_normal((C, P)) * cw
     z = rng.standard_normal((S, C, P))
     log_u = np.log(rng.random((S, C, P)))
-    eng = helpers.engine(pb, C, path)
+    eng = helpers.engine(pb, C, path, chains_per_block=cpb)
     eng.set_sampler(E.SAMPLER_CWMH, cw_scale=cw)
     eng.init_chains(x0, scale0=0.1)
     smp, llp, dec = eng.run_explicit(z.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
@@ -399,14 +401,15 @@ def test_componentwise_mh_matches_oracle_semantics(path):
 
 
 @pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
-def test_delayed_acceptance_matches_oracle_semantics(path):
+@pytest.mark.parametrize("cpb", [0, 48], ids=["auto", "one_batch"])   # one batch: the fine pass is compacted and packed densely
+def test_delayed_acceptance_matches_oracle_semantics(path, cpb):
     """DA (Christen & Fox 2005): coarse stage = every 5th time point."""
     from mcmc_mems_b200 import engine as E
     pb = helpers.load_problem("geometric")
     C, S, P, stride = 48, 12, 3, 5
     x0, xi, _ = _explicit_inputs(pb, C, S, 9)
     log_u = np.log(np.random.default_rng(10).random((S, C, 2)))
-    eng = helpers.engine(pb, C, path)
+    eng = helpers.engine(pb, C, path, chains_per_block=cpb)
     eng.set_sampler(E.SAMPLER_DA, da_stride=stride)
     eng.init_chains(x0, scale0=0.15)
     aux = eng.aux_state()
@@ -675,7 +678,8 @@ def test_sensitivity_push_forward_matches_oracle():
 
 
 @pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
-def test_delayed_acceptance_with_fft_coarse_surrogate(path):
+@pytest.mark.parametrize("cpb", [0, 44], ids=["auto", "one_batch"])
+def test_delayed_acceptance_with_fft_coarse_surrogate(path, cpb):
     """DA whose first stage is the reference's FFT surrogate + reconstruction (oracle/coarse.py): start-state coarse
     log-likelihoods and every two-stage decision replayed by the oracle (Q-factor problem, P = 4)."""
     from mcmc_mems_b200 import engine as E
@@ -685,7 +689,7 @@ def test_delayed_acceptance_with_fft_coarse_surrogate(path):
     C, S = 44, 12
     x0, xi, _ = _explicit_inputs(pb, C, S, 19, spread=0.3)      # wide: some chains start outside the prior box (-inf)
     log_u = np.log(np.random.default_rng(20).random((S, C, 2)))
-    eng = helpers.engine(pb, C, path)
+    eng = helpers.engine(pb, C, path, chains_per_block=cpb)
     eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
     eng.set_sampler(E.SAMPLER_DA, da_stride=0)
     eng.init_chains(x0, scale0=0.3)
