@@ -137,8 +137,9 @@ __device__ __forceinline__ void box_muller(unsigned int a, unsigned int b, doubl
 // The randomness of update `step` of global chain `gid`: four standard normals (Philox purpose 0)
 // and four log-uniforms (purpose 1).  RW/DA use xi = chol*z and log_u[0] (DA: also log_u[1] for
 // the second stage); CW uses z[p] and log_u[p] for component p.
+// n_lu: how many of the four log-uniforms the caller consumes (the double-precision log is the expensive part).
 __device__ __forceinline__ void draw_raw(unsigned long long seed, unsigned long long gid, unsigned long long step,
-                                         double* z, double* log_u) {
+                                         double* z, double* log_u, int n_lu = 4) {
     const unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
     const unsigned int c0 = (unsigned int)gid, c1 = (unsigned int)(gid >> 32);
     const unsigned int c2 = (unsigned int)step, c3 = (unsigned int)(step >> 32) & 0x00FFFFFFu;
@@ -147,9 +148,9 @@ __device__ __forceinline__ void draw_raw(unsigned long long seed, unsigned long 
     box_muller(n.x, n.y, z[0], z[1]);
     box_muller(n.z, n.w, z[2], z[3]);
     log_u[0] = log(((double)u.x + 1.0) * 2.3283064365386963e-10);   // u in (0, 1]
-    log_u[1] = log(((double)u.y + 1.0) * 2.3283064365386963e-10);
-    log_u[2] = log(((double)u.z + 1.0) * 2.3283064365386963e-10);
-    log_u[3] = log(((double)u.w + 1.0) * 2.3283064365386963e-10);
+    if (n_lu > 1) log_u[1] = log(((double)u.y + 1.0) * 2.3283064365386963e-10);
+    if (n_lu > 2) log_u[2] = log(((double)u.z + 1.0) * 2.3283064365386963e-10);
+    if (n_lu > 3) log_u[3] = log(((double)u.w + 1.0) * 2.3283064365386963e-10);
 }
 
 __device__ __forceinline__ void chol_mul(const MemsConsts& pb, const double* z, double* xi) {
@@ -271,7 +272,7 @@ __device__ __forceinline__ void batch_pre(ChainBatch& cb, const MemsConsts& pb, 
             for (int p = 0; p < P; ++p) z[p] = ra.xi[((size_t)s * P + p) * ch.C + c];
             for (int k = 0; k < ra.n_sub; ++k) lu[k] = ra.log_u[((size_t)s * ra.n_sub + k) * ch.C + c];
         } else {
-            draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, ra.step0 + (unsigned long long)s, z, lu);
+            draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, ra.step0 + (unsigned long long)s, z, lu, ra.n_sub);
             if (ra.mode != MEMS_MODE_CW) {
                 double xi[MEMS_PMAX];
                 chol_mul(pb, z, xi);

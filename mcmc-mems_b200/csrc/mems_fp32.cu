@@ -206,7 +206,7 @@ __global__ void draw_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, 
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int s = (int)(i / ch.C), c = (int)(i % ch.C);
         double z[4], lu[4], xi[MEMS_PMAX];
-        draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, step0 + (unsigned long long)s, z, lu);
+        draw_raw(ch.seed, ch.chain_id0 + (unsigned long long)c, step0 + (unsigned long long)s, z, lu, n_sub);
         if (mode == MEMS_MODE_CW) { for (int p = 0; p < pb.P; ++p) xi[p] = z[p]; }
         else chol_mul(pb, z, xi);
         if (xi_out)
