@@ -758,3 +758,29 @@ def test_rank_normalised_diagnostics_on_device_match_the_host_estimators():
     b = BatchedSamples(x.transpose(2, 1, 0), None, np.zeros(Cn), np.ones(Cn))
     assert np.allclose(b.compute_ess(on_device=True), b.compute_ess(on_device=False), rtol=1e-7)
     assert np.allclose(b.compute_rhat(on_device=True), b.compute_rhat(on_device=False), rtol=1e-9)
+
+
+def test_auxiliary_kernels_edge_sizes():
+    """Smallest legal inputs of the kernels either side of the path."""
+    from mcmc_mems_b200 import diagnostics as D, MemsError
+    from mcmc_mems_b200.engine import chain_autocov
+    rng = np.random.default_rng(23)
+    for n, P, Cn, L in ((4, 1, 1, 4), (5, 2, 3, 5), (64, 4, 17, 1), (33, 3, 40, 33)):
+        x = rng.standard_normal((n, P, Cn))
+        got = chain_autocov(torch.as_tensor(x, device="cuda"), L).cpu().numpy()
+        for p in range(P):
+            want = D._autocov(x[:, p, :].T)[:, :L].sum(axis=0)
+            assert np.allclose(got[p, :L], want, rtol=1e-10, atol=1e-12)
+    with pytest.raises(MemsError):
+        chain_autocov(torch.zeros(3, 1, 1, dtype=torch.float64, device="cuda"), 2)        # n_keep < 4
+    with pytest.raises(MemsError):
+        chain_autocov(torch.zeros(8, 1, 1, dtype=torch.float64, device="cuda"), 9)        # max_lag > n_keep
+    pb = helpers.load_problem("geometric")
+    eng = helpers.engine(pb, 1, 0)
+    x, cov, cost, its = eng.least_squares(pb["starts"][:1], max_iter=1)                   # one iteration: the start itself
+    assert np.allclose(x.cpu().numpy()[0], pb["starts"][0]) and its.cpu().numpy()[0] == 1
+    x, cov, cost, its = eng.least_squares(np.zeros((0, 3)))                               # no starts: empty outputs
+    assert x.shape == (0, 3) and cov.shape == (0, 3, 3)
+    with pytest.raises(ValueError):
+        eng.least_squares(pb["starts"], y_obs=np.zeros((2, len(pb["time"]))))              # 2 traces for 5 starts
+    eng.close()
