@@ -14,9 +14,6 @@
 #ifndef MEMS_TRYWAIT_HINT
 #define MEMS_TRYWAIT_HINT 0
 #endif
-#ifndef MEMS_EXP_EPI
-#define MEMS_EXP_EPI 0         // != 0: timing experiments with deliberately wrong numerics (never shipped)
-#endif
 #ifndef MEMS_EX2_MIX
 #define MEMS_EX2_MIX 0         // share of exponentials evaluated on the FMA pipe: 0 none, 1 -> 1/4, 2 -> 3/8, 3 -> 1/2
 #endif
@@ -308,28 +305,6 @@ __device__ __forceinline__ void epilogue_split_mix(const uint32_t* v, uint32_t (
 
 // 32 accumulator columns -> tanh -> fp16 hi/lo operand words (16 + 16 packed pairs)
 __device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
-#if MEMS_EXP_EPI == 1      // timing experiment only (wrong numerics): MUFU.TANH + one pack, no lo operand
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        float a, b;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(a) : "f"(__uint_as_float(v[2 * i])));
-        asm("tanh.approx.f32 %0, %1;" : "=f"(b) : "f"(__uint_as_float(v[2 * i + 1])));
-        hi2[i] = pack_half2(a, b);
-        lo2[i] = 0u;
-    }
-    return;
-#elif MEMS_EXP_EPI == 2    // timing experiment only: split + pack without tanh
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float t0_ = __uint_as_float(v[2 * i]), t1_ = __uint_as_float(v[2 * i + 1]);
-        const float h0 = __uint_as_float(v[2 * i] & 0xFFFFE000u), h1 = __uint_as_float(v[2 * i + 1] & 0xFFFFE000u);
-        float l0, l1;
-        upk(sub2(pk(t0_, t1_), pk(h0, h1)), l0, l1);
-        hi2[i] = pack_half2(h0, h1);
-        lo2[i] = pack_half2(l0, l1);
-    }
-    return;
-#endif
     epilogue_split_mix<MEMS_EX2_MIX>(v, hi2, lo2);
 }
 
