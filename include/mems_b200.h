@@ -15,7 +15,8 @@
  *     reaches the end of the enqueued work;
  *   - all work is enqueued on the cudaStream_t passed as `void* stream`
  *     (NULL = the legacy default stream); calls do not synchronise unless stated;
- *   - one handle per device, not thread-safe per handle;
+ *   - one handle per device, not thread-safe per handle; every call runs on the handle's device and
+ *     restores the caller's current CUDA device before it returns;
  *   - there is no CPU fallback: without a usable sm_100 device mems_create fails.
  *
  * Per-chain arrays are stored parameter-major, chain-minor ("[P][C]": element
@@ -75,7 +76,10 @@ int  mems_set_weights(mems_handle_t h, const float* const* W, const float* const
  * cuqi objects of identification.ipynb cell 10/14: Gaussian likelihood (y_obs, sigma2 = the
  * iid noise variance), Uniform prior (low, high) and the Gaussian proposal (chol = lower
  * Cholesky factor of its covariance, row-major P x P).                      HOST pointers.
- * time[T], scaler_mean[P+1], scaler_scale[P+1], y_obs[T], low[P], high[P], chol[P*P]. */
+ * time[T], scaler_mean[P+1], scaler_scale[P+1], y_obs[T], low[P], high[P], chol[P*P].
+ * Synchronous (blocking copies): no work of this handle may be in flight on any stream.  Chains initialised
+ * before the call are invalidated (their stored log-likelihoods belong to the old problem): call
+ * mems_init_chains again before mems_run. */
 int  mems_set_problem(mems_handle_t h, const double* time, const double* scaler_mean,
                       const double* scaler_scale, const double* y_obs, double sigma2,
                       const double* low, const double* high, const double* chol);
@@ -204,21 +208,6 @@ int  mems_lsq(mems_handle_t h, const double* x0_dev, int32_t n, const double* yo
               const double* bounds_lo, const double* bounds_hi, int32_t max_iter, double rel_step, double xtol,
               double ftol, double* x_out_dev, double* cov_out_dev, double* cost_out_dev, int32_t* iters_out_dev,
               void* stream);
-
-/* Hardware self-test of the tensor-core plumbing the MH kernels rely on (UMMA descriptors,
- * 128B swizzle, TMEM operand packing, tcgen05.ld/st, commit->mbarrier):
- * D[128][64] (f32) = A[128][64] (f16) * B[64][64]^T (f16), all device pointers, row-major.
- * variant 0: A operand written to TMEM by the threads (the product path), 1: A from shared memory,
- * 2: the split chain A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with A = [A_hi; A_lo] (256x64), B = [W_hi; W_lo] (128x64). */
-int  mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev,
-                        const void* b_f16_dev, float* d_out_dev, void* stream);
-
-/* Micro-benchmark of the epilogue building blocks (tools/microbench.py).  Modes 0..10 are listed above
- * the kernels in csrc/mems_microbench.cu (tcgen05.ld / tcgen05.st shapes, tanh and split arithmetic).  `blocks`
- * CTAs of `warps` warps run `iters` repetitions; cycles_out_dev [blocks] i64 = slowest thread of each CTA
- * (SM clocks), sink_dev [blocks*32*warps] u32 = scratch. */
-int  mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks,
-                     int64_t* cycles_out_dev, uint32_t* sink_dev, void* stream);
 
 /* Number of kernel launches issued through this handle since creation (bench bookkeeping). */
 int64_t mems_launch_count(mems_handle_t h);

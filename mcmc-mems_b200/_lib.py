@@ -24,7 +24,7 @@ SAMPLER_DA = 2
 EXPORTS = [
     "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
     "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
-    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_selftest_umma", "mems_microbench", "mems_lsq", "mems_chain_autocov", "mems_set_coarse_fft",
+    "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_lsq", "mems_chain_autocov", "mems_set_coarse_fft",
 ]
 
 
@@ -72,8 +72,6 @@ def lib():
     L.mems_chain_moments.argtypes = [i32, vp, i32, i32, i32, vp, vp]
     L.mems_launch_count.argtypes = [vp]
     L.mems_launch_count.restype = i64
-    L.mems_selftest_umma.argtypes = [i32, i32, vp, vp, vp, vp]
-    L.mems_microbench.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
     L.mems_lsq.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp]
     L.mems_chain_autocov.argtypes = [i32, vp, i32, i32, i32, i32, vp, vp]
     L.mems_set_coarse_fft.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp]
@@ -84,4 +82,31 @@ def lib():
 def check(rc: int, what: str):
     if rc != 0:
         msg = lib().mems_last_error().decode("utf-8", "replace")
+        raise MemsError(f"{what} failed (code {rc}): {msg}")
+
+
+# -- development tools (tools/libmems_b200_tools.so; not part of the product ABI) -----------------
+TOOLS_LIB_PATH = os.environ.get("MEMS_TOOLS_LIB") or os.path.join(os.path.dirname(_HERE), "tools", "libmems_b200_tools.so")
+_tools = None
+
+
+def tools_lib():
+    """Micro-benchmarks and the UMMA self-test (tools/mems_b200_tools.h)."""
+    global _tools
+    if _tools is not None:
+        return _tools
+    if not os.path.exists(TOOLS_LIB_PATH):
+        raise MemsError(f"{TOOLS_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = C.CDLL(TOOLS_LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int32
+    L.mems_tools_last_error.restype = C.c_char_p
+    L.mems_tools_selftest_umma.argtypes = [i32, i32, vp, vp, vp, vp]
+    L.mems_tools_microbench.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp]
+    _tools = L
+    return L
+
+
+def check_tools(rc: int, what: str):
+    if rc != 0:
+        msg = tools_lib().mems_tools_last_error().decode("utf-8", "replace")
         raise MemsError(f"{what} failed (code {rc}): {msg}")

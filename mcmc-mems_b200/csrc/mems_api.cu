@@ -41,6 +41,26 @@ int fail(int code, const char* fmt, ...) {
             return fail(MEMS_E_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));           \
     } while (0)
 
+// Every entry point runs on the handle's device and puts the caller's current device back on exit (PyTorch reads the
+// current device from the runtime: an engine on cuda:1 must not change what `device="cuda"` means for the caller).
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err != cudaSuccess) { prev = -1; return; }
+        if (prev != dev) err = cudaSetDevice(dev);
+        else prev = -1;                                // nothing to restore
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define DEVICE_SCOPE(dev)                                                                            \
+    DeviceScope device_scope_(dev);                                                                  \
+    if (device_scope_.err != cudaSuccess)                                                            \
+        return fail(MEMS_E_CUDA, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(device_scope_.err))
+
 }  // namespace
 
 struct MemsHandle_ {
@@ -146,7 +166,7 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
         if (cfg->n_time > tmax)
             return fail(MEMS_E_INVALID, "n_time=%d does not fit in shared memory on this path (max %d)", cfg->n_time, tmax);
     }
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    DEVICE_SCOPE(cfg->device);
     MemsHandle_* h = new (std::nothrow) MemsHandle_();
     if (!h) return fail(MEMS_E_INVALID, "out of host memory");
     h->cfg = *cfg;
@@ -184,7 +204,7 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
 
 void mems_destroy(mems_handle_t h) {
     if (!h) return;
-    cudaSetDevice(h->cfg.device);
+    DeviceScope device_scope_(h->cfg.device);
     cudaFree(h->dev_pb); cudaFree(h->dev_ts); cudaFree(h->dev_yobs); cudaFree(h->dev_wimg);
     cudaFree(h->chains.x); cudaFree(h->chains.ll); cudaFree(h->chains.scale); cudaFree(h->chains.lambda);
     cudaFree(h->chains.win_acc); cudaFree(h->chains.adapt_i); cudaFree(h->chains.acc_count);
@@ -199,7 +219,7 @@ int mems_set_weights(mems_handle_t h, const float* const* W, const float* const*
     if (!h || !W || !b) return fail(MEMS_E_INVALID, "null argument");
     for (int l = 0; l <= MEMS_HIDDEN; ++l)
         if (!W[l] || !b[l]) return fail(MEMS_E_INVALID, "null weight pointer for layer %d", l);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     MemsProblem& pb = h->host_pb;
     const int P = pb.c.P;
     memcpy(pb.W1, W[0], sizeof(float) * (P + 1) * MEMS_WIDTH);
@@ -222,7 +242,7 @@ int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_m
     if (!h || !time || !scaler_mean || !scaler_scale || !y_obs || !low || !high || !chol)
         return fail(MEMS_E_INVALID, "null argument");
     if (!(sigma2 > 0.0)) return fail(MEMS_E_INVALID, "sigma2 must be positive");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     MemsProblem& pb = h->host_pb;
     const int P = pb.c.P, T = pb.c.T;
     for (int p = 0; p <= P; ++p) {
@@ -245,6 +265,7 @@ int mems_set_problem(mems_handle_t h, const double* time, const double* scaler_m
     CUDA_TRY(cudaMemcpy(h->dev_yobs, y_obs, sizeof(double) * T, cudaMemcpyHostToDevice));
     h->host_yobs.assign(y_obs, y_obs + T);
     h->have_problem = true;
+    h->have_chains = false;      // chains.ll / chains.llc were scored against the previous y_obs / sigma2 / bounds
     const int rc = upload_coarse(h);                       // the coarse stage scores the same observation
     if (rc != MEMS_OK) return rc;
     return upload_problem(h);
@@ -256,7 +277,7 @@ int mems_forward(mems_handle_t h, const double* x_dev, int32_t n, float* y_out, 
     if (n < 0) return fail(MEMS_E_INVALID, "n < 0");
     if (n == 0) return MEMS_OK;
     if (!x_dev) return fail(MEMS_E_INVALID, "null argument");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_forward(ctx, x_dev, n, y_out, loglik_out, 0, 1)
                                                 : mems_fp32_forward(ctx, x_dev, n, y_out, loglik_out, 0, 1);
@@ -317,7 +338,7 @@ int mems_set_coarse_fft(mems_handle_t h, const float* const* W, const float* con
     if (!h || !W || !b || !scaler_mean || !scaler_scale) return fail(MEMS_E_INVALID, "null argument");
     for (int i = 0; i < MEMS_HIDDEN + 1; ++i)
         if (!W[i] || !b[i]) return fail(MEMS_E_INVALID, "null weight pointer for layer %d", i);
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     const int P = h->host_pb.c.P;
     if (!h->host_coarse) {
         h->host_coarse = new (std::nothrow) MemsCoarse();
@@ -353,7 +374,7 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
     if (!h || !x0_dev) return fail(MEMS_E_INVALID, "null argument");
     if (!h->have_weights || !h->have_problem) return fail(MEMS_E_STATE, "set weights and problem first");
     if (!(scale0 > 0.0)) return fail(MEMS_E_INVALID, "scale0 must be positive");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     h->chains.seed = seed;
     h->chains.chain_id0 = chain_id0;
     h->steps_done = 0;
@@ -381,7 +402,7 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
 }
 
 static int run_common(mems_handle_t h, MemsRunArgs& ra, void* stream) {
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     ra.step0 = h->steps_done;
     ra.nc = choose_nc(h, h->chains.C);
     ra.mode = h->sampler;
@@ -429,7 +450,7 @@ int mems_draw(mems_handle_t h, uint64_t step0, int32_t n_steps, double* xi_out, 
     if (!h) return fail(MEMS_E_INVALID, "null handle");
     if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
     if (n_steps <= 0) return MEMS_OK;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = mems_draw_launch(ctx, h->sampler, n_sub, step0, n_steps, xi_out, log_u_out);
     h->launches += 1;
@@ -441,7 +462,7 @@ int mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale, ui
                    uint64_t* steps_done, void* stream) {
     if (!h) return fail(MEMS_E_INVALID, "null handle");
     if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.c.P;
     if (x) CUDA_TRY(cudaMemcpyAsync(x, h->chains.x, sizeof(double) * P * C, cudaMemcpyDeviceToDevice, st));
@@ -459,7 +480,7 @@ int mems_get_state(mems_handle_t h, double* x, double* loglik, double* scale, ui
 int mems_get_aux(mems_handle_t h, double* scale_cw, double* loglik_coarse, uint32_t* promote_count, void* stream) {
     if (!h) return fail(MEMS_E_INVALID, "null handle");
     if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t C = (size_t)h->chains.C, P = (size_t)h->host_pb.c.P;
     if (scale_cw) CUDA_TRY(cudaMemcpyAsync(scale_cw, h->chains.scale_cw, sizeof(double) * P * C, cudaMemcpyDeviceToDevice, st));
@@ -480,7 +501,7 @@ int mems_mlp_forward(int32_t device, int32_t n_layers, const int32_t* widths, co
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
-    CUDA_TRY(cudaSetDevice(device));
+    DEVICE_SCOPE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -510,7 +531,7 @@ int mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_keep
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
-    CUDA_TRY(cudaSetDevice(device));
+    DEVICE_SCOPE(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     const int e = mems_chain_moments_launch(samples_dev, n_keep, n_params, n_chains, out_dev, prop.multiProcessorCount,
@@ -539,7 +560,7 @@ int mems_lsq(mems_handle_t h, const double* x0_dev, int32_t n, const double* yob
         b[MEMS_PMAX + p] = bounds_hi ? bounds_hi[p] : h->host_pb.c.high[p];
         if (!(b[p] < b[MEMS_PMAX + p])) return fail(MEMS_E_INVALID, "bounds of parameter %d are empty", p);
     }
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    DEVICE_SCOPE(h->cfg.device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t wbytes = mems_lsq_workspace_bytes(n, P, T) + 16 * 256;
     void* ws = nullptr;
@@ -572,7 +593,7 @@ int mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
-    CUDA_TRY(cudaSetDevice(device));
+    DEVICE_SCOPE(device);
     const size_t wbytes = mems_acov_workspace_bytes(n_keep, n_params, n_chains, max_lag);
     if (wbytes == 0) return fail(MEMS_E_INVALID, "n_keep=%d too long for the shared-memory autocovariance kernel (max 20480)", n_keep);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -584,27 +605,6 @@ int mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep
     return MEMS_OK;
 }
 
-int mems_microbench(int32_t device, int32_t mode, int32_t warps, int32_t iters, int32_t blocks, int64_t* cycles_out_dev,
-                    uint32_t* sink_dev, void* stream) {
-    if (!cycles_out_dev || !sink_dev) return fail(MEMS_E_INVALID, "null argument");
-    if (mode < 0 || ((mode > 19 && mode < 20) || (mode > 29 && mode != 100 && mode != 101)) || warps < 1 || warps > 32 || (mode <= 29 && warps > 16) || iters < 1 || blocks < 1) return fail(MEMS_E_INVALID, "bad microbench arguments");
-    CUDA_TRY(cudaSetDevice(device));
-    const int e = mems_tc_microbench(mode, warps, iters, blocks, reinterpret_cast<long long*>(cycles_out_dev), sink_dev,
-                                     reinterpret_cast<cudaStream_t>(stream));
-    if (e != 0) return fail(MEMS_E_CUDA, "microbench launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    return MEMS_OK;
-}
-
 int64_t mems_launch_count(mems_handle_t h) { return h ? h->launches : 0; }
-
-int mems_selftest_umma(int32_t device, int32_t variant, const void* a_f16_dev, const void* b_f16_dev, float* d_out_dev,
-                       void* stream) {
-    if (!a_f16_dev || !b_f16_dev || !d_out_dev) return fail(MEMS_E_INVALID, "null argument");
-    if (variant < 0 || variant > 2) return fail(MEMS_E_INVALID, "variant must be 0 (A in TMEM), 1 (A in shared memory) or 2 (split chain)");
-    CUDA_TRY(cudaSetDevice(device));
-    const int e = mems_tc_selftest(variant, a_f16_dev, b_f16_dev, d_out_dev, reinterpret_cast<cudaStream_t>(stream));
-    if (e != 0) return fail(MEMS_E_CUDA, "selftest launch failed: %s", cudaGetErrorString((cudaError_t)e));
-    return MEMS_OK;
-}
 
 }  // extern "C"

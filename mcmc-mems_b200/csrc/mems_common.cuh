@@ -522,8 +522,6 @@ int mems_tc_choose_nc(int C, int T, int sm_count);
 int mems_tc_max_time_points(size_t smem_optin);
 int mems_fp32_max_time_points(size_t smem_optin);
 int mems_fp32_choose_nc(int C, int T, int sm_count);
-int mems_tc_microbench(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st);
-int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st);
 int mems_coarse_ll_launch(const MemsLaunchCtx& ctx, const MemsCoarse* cm_dev, const double* x_dev, int n, double* ll_out);
 int mems_draw_launch(const MemsLaunchCtx& ctx, int mode, int n_sub, unsigned long long step0, int n_steps,
                      double* xi_out, double* log_u_out);

@@ -200,17 +200,18 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     mbar_wait(&gs.bar_D[s], (phD >> s) & 1u);
                     phD ^= (1u << s);
                     tc_fence_after();
-                    uint32_t v[NCOL];
-#pragma unroll
-                    for (int c = 0; c < NCOL / 32; ++c) tmem_ld32(tD + NCOL * h + 32 * c, v + 32 * c);
-                    tc_wait_ld();
+                    // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer
+                    // grain than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
+                    constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
                     if (layer < MEMS_HIDDEN - 1) {
 #pragma unroll
-                        for (int c = 0; c < NCOL / 32; ++c) {
-                            uint32_t hi2[16], lo2[16];
-                            epilogue_split(v + 32 * c, hi2, lo2);
-                            tmem_st16(tD + 64 + (NCOL / 2) * h + 16 * c, hi2);
-                            tmem_st16(tD + 96 + (NCOL / 2) * h + 16 * c, lo2);
+                        for (int pc = 0; pc < NCOL / EC; ++pc) {
+                            uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
+                            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                            tc_wait_ld();
+                            epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
+                            tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
+                            tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
                         }
                         tc_wait_st();
                         tc_fence_before();
@@ -218,7 +219,14 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     } else {
                         uint64_t acc = pk(0.0f, 0.0f);
 #pragma unroll
-                        for (int c = 0; c < NCOL / 32; ++c) acc = epilogue_dot(v + 32 * c, sm.w7 + NCOL * h + 32 * c, acc);
+                        for (int pc = 0; pc < NCOL / EC; ++pc) {
+                            uint32_t w[EC];
+                            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                            tc_wait_ld();
+#pragma unroll
+                            for (int g8 = 0; g8 < EC / 8; ++g8)
+                                acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
+                        }
                         float oa, ob;
                         upk(acc, oa, ob);
                         float o = oa + ob;
@@ -471,113 +479,6 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     tc_epilogue_free<NH>(sm);
 }
 
-// ------------------------------------------------------------------------------------------
-// Self-test: D[128][64] = A[128][64] * B[64][64]^T through the same descriptors / TMEM paths.
-//   variant 0: A from TMEM (tcgen05.st packed fp16), variant 1: A from shared memory (SS form).
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sw128_offset(int row, int k) {   // byte offset of element (row, k) in a block
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) & 7) << 4) + (k & 7) * 2);
-}
-
-__global__ void __launch_bounds__(160, 1)
-umma_selftest_kernel(int variant, const __half* __restrict__ A, const __half* __restrict__ B, float* __restrict__ D) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* sB = smem_raw;                    // 8 KB
-    unsigned char* sA = smem_raw + BLK;              // 16 KB
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 3 * BLK);
-    uint32_t* tbase = reinterpret_cast<uint32_t*>(smem_raw + 3 * BLK + 16);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-    for (int i = tid; i < 64 * 64; i += blockDim.x) {
-        const int n = i >> 6, k = i & 63;
-        *reinterpret_cast<__half*>(sB + sw128_offset(n, k)) = B[i];
-    }
-    if (variant == 2) {          // split chain: A = [A_hi; A_lo] (256 x 64), B = [W_hi; W_lo] (128 x 64)
-        for (int i = tid; i < 64 * 64; i += blockDim.x) {
-            const int n = i >> 6, k = i & 63;
-            *reinterpret_cast<__half*>(sA + sw128_offset(n, k)) = B[64 * 64 + i];
-        }
-    } else {
-        for (int i = tid; i < 128 * 64; i += blockDim.x) {
-            const int m = i >> 6, k = i & 63;
-            *reinterpret_cast<__half*>(sA + sw128_offset(m, k)) = A[i];
-        }
-    }
-    fence_proxy_async();
-    __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase)), "r"(128) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t base = *tbase;
-    if (warp < 4) {
-        const uint32_t tl = base + ((uint32_t)(warp * 32) << 16);
-        if (variant == 0 || variant == 2) {
-            const int m = warp * 32 + lane;
-            const int nparts = (variant == 2) ? 2 : 1;
-            for (int part = 0; part < nparts; ++part) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t w[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int k = 32 * c + 2 * i;
-                        const __half* src = A + (size_t)(part * 128 + m) * 64 + k;
-                        w[i] = (uint32_t)__half_as_ushort(src[0]) | ((uint32_t)__half_as_ushort(src[1]) << 16);
-                    }
-                    tmem_st16(tl + 64 + 32 * part + 16 * c, w);
-                }
-            }
-            tc_wait_st();
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 4 && lane == 0) {
-        tc_fence_after();
-        const uint64_t b = make_desc(smem_u32(sB));
-        const uint64_t a = make_desc(smem_u32(sA));
-        if (variant == 2) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_ts(base, base + 64 + 8 * ks, b + 2 * ks, ks > 0 ? 1u : 0u);   // hi*hi
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_ts(base, base + 96 + 8 * ks, b + 2 * ks, 1u);                 // lo*hi
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_ts(base, base + 64 + 8 * ks, a + 2 * ks, 1u);                 // hi*lo
-        } else {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                if (variant == 0) umma_ts(base, base + 64 + 8 * ks, b + 2 * ks, ks > 0 ? 1u : 0u);
-                else umma_ss(base, a + 2 * ks, b + 2 * ks, ks > 0 ? 1u : 0u);
-            }
-        }
-        umma_commit(bar);
-    }
-    if (warp < 4) {
-        mbar_wait(bar, 0);
-        tc_fence_after();
-        const uint32_t tl = base + ((uint32_t)(warp * 32) << 16);
-        const int m = warp * 32 + lane;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tl + 32 * c, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) D[m * 64 + 32 * c + i] = __uint_as_float(v[i]);
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(128) : "memory");
-    }
-}
-
 size_t tc_smem_bytes(int T) { return sizeof(TcSmem) + (size_t)T * (sizeof(double) + sizeof(float)) + 16; }
 
 // host-side fp16 helpers (round to nearest even through the CUDA host implementation)
@@ -708,13 +609,3 @@ int mems_tc_forward(const MemsLaunchCtx& ctx, const double* x_dev, int n, float*
     return launch_by_p<2>(ctx.pb_host->c.P, tc_forward_kernel<1, 2>, tc_forward_kernel<2, 2>, tc_forward_kernel<3, 2>,
                           tc_forward_kernel<4, 2>, gr, smem, ctx.stream, ctx.pb_dev, x_dev, n, nc, y_out, ll_out, apply_prior, t_stride);
 }
-
-int mems_tc_selftest(int variant, const void* a_f16, const void* b_f16, float* d_out, cudaStream_t st) {
-    const size_t smem = 3 * BLK + 64;
-    cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    umma_selftest_kernel<<<1, 160, smem, st>>>(variant, static_cast<const __half*>(a_f16),
-                                               static_cast<const __half*>(b_f16), d_out);
-    return (int)cudaGetLastError();
-}
-

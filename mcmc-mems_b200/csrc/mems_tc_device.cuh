@@ -15,7 +15,17 @@
 #define MEMS_TRYWAIT_HINT 0
 #endif
 #ifndef MEMS_EX2_MIX
-#define MEMS_EX2_MIX 0         // share of exponentials evaluated on the FMA pipe: 0 none, 1 -> 1/4, 2 -> 3/8, 3 -> 1/2
+#define MEMS_EX2_MIX 0         // (round-1 arithmetic, micro-benchmarks only) share of exponentials on the FMA pipe
+#endif
+// Product-kernel epilogue knobs (A/B builds through __graft_entry__.build_variant):
+#ifndef MEMS_EPI_COLS
+#define MEMS_EPI_COLS 8        // accumulator columns a thread loads, transforms and stores at a time: 8, 16 or 32
+#endif
+#ifndef MEMS_EPI_R16
+#define MEMS_EPI_R16 0         // 1: one reciprocal per sixteen activations (needs MEMS_EPI_COLS >= 16)
+#endif
+#ifndef MEMS_EPI_POLY8
+#define MEMS_EPI_POLY8 0       // eighths of the exponentials evaluated on the FMA pipe: 0, 1, 2 or 4
 #endif
 
 namespace {
@@ -183,6 +193,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
           "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -191,6 +212,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* v);
+template <> __device__ __forceinline__ void tmem_ld_n<8>(uint32_t taddr, uint32_t* v) { tmem_ld8(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t* v) { tmem_ld16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t* v) { tmem_ld32(taddr, v); }
+template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* v);
+template <> __device__ __forceinline__ void tmem_st_n<4>(uint32_t taddr, const uint32_t* v) { tmem_st4(taddr, v); }
+template <> __device__ __forceinline__ void tmem_st_n<8>(uint32_t taddr, const uint32_t* v) { tmem_st8(taddr, v); }
+template <> __device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t* v) {
+    tmem_st16(taddr, *reinterpret_cast<const uint32_t(*)[16]>(v));
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -289,6 +321,123 @@ __device__ __forceinline__ void split_pack8(const uint64_t (&T)[4], uint32_t* hi
     }
 }
 
+// ---- round-2 epilogue arithmetic ---------------------------------------------------------------------------
+// Measured (tools/microbench_pipes.py, profiles/r02_microbench_pipes.log): the epilogue is bound by instruction issue
+// on the FMA + ALU pipes together, not by the XU pipe alone -- LOP3 / F2FP / packed FP32x2 cost two pipe cycles each and
+// LOP3 does not overlap with FFMA2.  Two changes take 1.9 of 9.75 scalar-op slots per activation out:
+//   * the factor 2 of |tanh| = 2/(1+q) - 1 is folded into the shared reciprocal, so the last level of the product tree
+//     IS the FMA that produces the result (4 packed multiplies per eight activations fewer);
+//   * hi = RN_f16(t) comes straight from the pack instruction and lo = t - hi from ONE mixed-precision add
+//     (add.rn.f32.f16 -> FHADD with the half selector and the negation as operand modifiers): no mask, no separate
+//     subtraction.  hi is now rounded to nearest instead of truncated, so |lo| <= 2^-12 |t|.
+// NPOLY (0..2) of the four element pairs take 2^-|y| from the FMA pipe (ex2_neg_abs_poly2) instead of the XU pipe.
+template <int NPOLY = 0>
+__device__ __forceinline__ void tanh8_fold(const uint32_t* v, uint64_t (&T)[4]) {
+    uint64_t Q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < NPOLY) Q[i] = ex2_neg_abs_poly2(v[i], v[i + 4]);
+        else Q[i] = pk(ex2_approx(-fabsf(__uint_as_float(v[i]))), ex2_approx(-fabsf(__uint_as_float(v[i + 4]))));
+    }
+    const uint64_t one2 = pk(1.0f, 1.0f), m1 = pk(-1.0f, -1.0f);
+    const uint64_t A0 = add2(Q[0], one2), A1 = add2(Q[1], one2), A2 = add2(Q[2], one2), A3 = add2(Q[3], one2);
+    const uint64_t B0 = mul2(A0, A1), B1 = mul2(A2, A3);
+    float P0, P1;
+    upk(mul2(B0, B1), P0, P1);
+    const float r = rcp_approx(P0 * P1);
+    const float r2 = r + r;
+    const uint64_t Rq = pk(r2 * P1, r2 * P0);                      // (2 / prod of lane 0, 2 / prod of lane 1)
+    const uint64_t Rb0 = mul2(Rq, B1), Rb1 = mul2(Rq, B0);        // 2 / (a0 a1), 2 / (a2 a3)
+    const uint64_t U0 = fma2(Rb0, A1, m1), U1 = fma2(Rb0, A0, m1), U2 = fma2(Rb1, A3, m1), U3 = fma2(Rb1, A2, m1);
+    float a, b;
+    upk(U0, a, b); T[0] = pk(copysignf(a, __uint_as_float(v[0])), copysignf(b, __uint_as_float(v[4])));
+    upk(U1, a, b); T[1] = pk(copysignf(a, __uint_as_float(v[1])), copysignf(b, __uint_as_float(v[5])));
+    upk(U2, a, b); T[2] = pk(copysignf(a, __uint_as_float(v[2])), copysignf(b, __uint_as_float(v[6])));
+    upk(U3, a, b); T[3] = pk(copysignf(a, __uint_as_float(v[3])), copysignf(b, __uint_as_float(v[7])));
+}
+
+// Sixteen activations behind ONE reciprocal (1.0625 XU operations per activation instead of 1.125): two groups of
+// eight with the layout of tanh8_fold; the sixteen denominators lie in (1, 2], their product in (1, 65536].
+template <int NPOLY = 0>
+__device__ __forceinline__ void tanh16_fold(const uint32_t* v, uint64_t (&T)[8]) {
+    uint64_t A[8];
+    const uint64_t one2 = pk(1.0f, 1.0f), m1 = pk(-1.0f, -1.0f);
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t ya = v[8 * g + i], yb = v[8 * g + i + 4];
+            uint64_t q;
+            if (g == 0 && i < NPOLY) q = ex2_neg_abs_poly2(ya, yb);
+            else q = pk(ex2_approx(-fabsf(__uint_as_float(ya))), ex2_approx(-fabsf(__uint_as_float(yb))));
+            A[4 * g + i] = add2(q, one2);
+        }
+    const uint64_t B0 = mul2(A[0], A[1]), B1 = mul2(A[2], A[3]), B2 = mul2(A[4], A[5]), B3 = mul2(A[6], A[7]);
+    const uint64_t C0 = mul2(B0, B1), C1 = mul2(B2, B3);
+    float P0, P1;
+    upk(mul2(C0, C1), P0, P1);
+    const float r = rcp_approx(P0 * P1);
+    const float r2 = r + r;
+    const uint64_t Rq = pk(r2 * P1, r2 * P0);
+    const uint64_t Rc0 = mul2(Rq, C1), Rc1 = mul2(Rq, C0);        // 2 / C0, 2 / C1
+    const uint64_t Rb0 = mul2(Rc0, B1), Rb1 = mul2(Rc0, B0), Rb2 = mul2(Rc1, B3), Rb3 = mul2(Rc1, B2);
+    const uint64_t U[8] = {fma2(Rb0, A[1], m1), fma2(Rb0, A[0], m1), fma2(Rb1, A[3], m1), fma2(Rb1, A[2], m1),
+                           fma2(Rb2, A[5], m1), fma2(Rb2, A[4], m1), fma2(Rb3, A[7], m1), fma2(Rb3, A[6], m1)};
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a, b;
+            upk(U[4 * g + i], a, b);
+            T[4 * g + i] = pk(copysignf(a, __uint_as_float(v[8 * g + i])), copysignf(b, __uint_as_float(v[8 * g + i + 4])));
+        }
+}
+
+// (ta, tb) -> packed fp16 pair hi2 = RN(ta, tb) (ta in the low half) and lo2 = RN(ta - hi_a, tb - hi_b)
+__device__ __forceinline__ void split_pair_rn(float ta, float tb, uint32_t& hi2, uint32_t& lo2) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(tb), "f"(ta));
+    float la, lb;
+    asm("{\n\t.reg .b16 h0, h1, n0, n1;\n\tmov.b32 {h0, h1}, %2;\n\t"
+        "neg.f16 n0, h0;\n\tneg.f16 n1, h1;\n\t"
+        "add.rn.f32.f16 %0, n0, %3;\n\t"
+        "add.rn.f32.f16 %1, n1, %4;\n\t}"
+        : "=f"(la), "=f"(lb) : "r"(hi2), "f"(ta), "f"(tb));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(lb), "f"(la));
+}
+
+// hi/lo operand words 4g..4g+3 of eight tanh values (T[i] = (t_i, t_{i+4})); word w holds elements 2w, 2w+1
+__device__ __forceinline__ void split_pack8_rn(const uint64_t (&T)[4], uint32_t* hi2, uint32_t* lo2) {
+    float t[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) upk(T[i], t[i], t[i + 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pair_rn(t[2 * i], t[2 * i + 1], hi2[i], lo2[i]);
+}
+
+// NG groups of eight accumulator columns -> tanh -> fp16 hi/lo operand words (4*NG + 4*NG packed pairs).
+// R16: groups of eight share a reciprocal pairwise (NG even).  POLY8: exponentials per 8 (R16: per 16) activations that
+// are evaluated on the FMA pipe, in eighths: 0, 1 (odd groups only: one pair of every other group), 2, 4.
+template <int NG, bool R16 = false, int POLY8 = 0>
+__device__ __forceinline__ void epilogue_split_v2(const uint32_t* v, uint32_t* hi2, uint32_t* lo2) {
+    if (R16) {
+#pragma unroll
+        for (int g = 0; g < NG; g += 2) {
+            uint64_t T[8];
+            tanh16_fold<POLY8>(&v[8 * g], T);
+            split_pack8_rn(*reinterpret_cast<uint64_t(*)[4]>(&T[0]), &hi2[4 * g], &lo2[4 * g]);
+            split_pack8_rn(*reinterpret_cast<uint64_t(*)[4]>(&T[4]), &hi2[4 * g + 4], &lo2[4 * g + 4]);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint64_t T[4];
+            if (POLY8 == 1) { if (g & 1) tanh8_fold<1>(&v[8 * g], T); else tanh8_fold<0>(&v[8 * g], T); }
+            else tanh8_fold<POLY8 / 2>(&v[8 * g], T);
+            split_pack8_rn(T, &hi2[4 * g], &lo2[4 * g]);
+        }
+    }
+}
+
 // MIX: share of exponentials on the FMA pipe: 0 -> none, 1 -> 1/4, 2 -> 3/8 (groups alternate 2,1 pairs), 3 -> 1/2
 template <int MIX>
 __device__ __forceinline__ void epilogue_split_mix(const uint32_t* v, uint32_t (&hi2)[16], uint32_t (&lo2)[16]) {
@@ -308,7 +457,17 @@ __device__ __forceinline__ void epilogue_split(const uint32_t* v, uint32_t (&hi2
     epilogue_split_mix<MEMS_EX2_MIX>(v, hi2, lo2);
 }
 
-// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights.
+// 16 accumulator columns -> tanh -> fp16 hi/lo operand words (8 + 8 packed pairs)
+__device__ __forceinline__ void epilogue_split16(const uint32_t* v, uint32_t* hi2, uint32_t* lo2) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint64_t T[4];
+        tanh8_mix<0>(&v[8 * g], T);
+        split_pack8(T, &hi2[4 * g], &lo2[4 * g]);
+    }
+}
+
+// 32 accumulator columns of the last tanh layer -> dot with the 64->1 output weights (round-1 arithmetic; micro-benchmarks).
 // w7p holds the weights permuted per group of eight as (w0,w4, w1,w5, w2,w6, w3,w7) to match tanh8's pairing.
 __device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float* w7p, uint64_t acc) {
 #pragma unroll
@@ -322,6 +481,19 @@ __device__ __forceinline__ uint64_t epilogue_dot(const uint32_t* v, const float*
         acc = fma2(T[2], pk(wb.x, wb.y), acc);
         acc = fma2(T[3], pk(wb.z, wb.w), acc);
     }
+    return acc;
+}
+
+// Eight accumulator columns of the last tanh layer -> dot with eight of the 64->1 output weights (same permutation).
+__device__ __forceinline__ uint64_t epilogue_dot8(const uint32_t* v, const float* w7p, uint64_t acc) {
+    uint64_t T[4];
+    tanh8_fold<0>(v, T);
+    const float4 wa = *reinterpret_cast<const float4*>(w7p);
+    const float4 wb = *reinterpret_cast<const float4*>(w7p + 4);
+    acc = fma2(T[0], pk(wa.x, wa.y), acc);
+    acc = fma2(T[1], pk(wa.z, wa.w), acc);
+    acc = fma2(T[2], pk(wb.x, wb.y), acc);
+    acc = fma2(T[3], pk(wb.z, wb.w), acc);
     return acc;
 }
 

@@ -64,9 +64,9 @@ def test_umma_selftest(variant):
     A = (torch.randn(128, 64, generator=g)).half().cuda()
     B = (torch.randn(64, 64, generator=g)).half().cuda()
     D = torch.full((128, 64), float("nan"), device="cuda")
-    rc = _lib.lib().mems_selftest_umma(0, variant, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+    rc = _lib.tools_lib().mems_tools_selftest_umma(0, variant, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
                                        ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-    _lib.check(rc, "mems_selftest_umma")
+    _lib.check_tools(rc, "mems_tools_selftest_umma")
     torch.cuda.synchronize()
     want = A.float() @ B.float().t()
     err = (D - want).abs().max().item()

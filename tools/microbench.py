@@ -13,7 +13,7 @@ import __graft_entry__ as g  # noqa: E402
 g.build()
 from mcmc_mems_b200 import _lib  # noqa: E402
 
-L = _lib.lib()
+L = _lib.tools_lib()
 blocks, iters = 148, 400
 if os.environ.get("MB_STAGGER"):
     iters = 401                # odd: warps of an SMSP start a quarter iteration apart (de-phased)
@@ -49,8 +49,8 @@ for mode, (name, nbytes, nact) in MODES.items():
         cyc = torch.zeros(blocks, dtype=torch.int64, device="cuda")
         sink = torch.zeros(blocks * 32 * warps, dtype=torch.int32, device="cuda")
         for rep in range(2):
-            _lib.check(L.mems_microbench(0, mode, warps, iters, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_microbench")
+            _lib.check_tools(L.mems_tools_microbench(0, mode, warps, iters, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_tools_microbench")
         torch.cuda.synchronize()
         c = cyc.double().median().item()
         per_iter_sm = c / iters                      # cycles for `warps` warp-iterations on one SM
@@ -70,8 +70,8 @@ for mode, (name, nops) in PROBES.items():
         cyc = torch.zeros(blocks, dtype=torch.int64, device="cuda")
         sink = torch.zeros(blocks * 32 * warps, dtype=torch.int32, device="cuda")
         for rep in range(2):
-            _lib.check(L.mems_microbench(0, mode, warps, 2000, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_microbench")
+            _lib.check_tools(L.mems_tools_microbench(0, mode, warps, 2000, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_tools_microbench")
         torch.cuda.synchronize()
         c = cyc.double().median().item() / 2000
         print(f"probe {mode} {name:24s} warps {warps:2d}: {c / nops / (warps / 4):6.2f} SMSP-cycles per warp-op (group)")
@@ -83,8 +83,8 @@ for mode, where in ((100, "TMEM"), (101, "smem")) if len(sys.argv) <= 1 else ():
         sink = torch.zeros(64, dtype=torch.int32, device="cuda")
         it = 256
         for rep in range(2):
-            _lib.check(L.mems_microbench(0, mode, n // 8, it, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
-                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_microbench")
+            _lib.check_tools(L.mems_tools_microbench(0, mode, n // 8, it, blocks, C.c_void_p(cyc.data_ptr()), C.c_void_p(sink.data_ptr()),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mems_tools_microbench")
         torch.cuda.synchronize()
         c = cyc.double().median().item() / (4 * it)
         print(f"mma M=128 N={n:3d} K=16 A in {where}: {c:6.1f} cyc/MMA -> {2 * 128 * n * 16 / c:7.0f} FLOP/clk/SM")

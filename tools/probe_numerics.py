@@ -24,7 +24,7 @@ def selftest(variant, A, B):
     A = A.half().cuda().contiguous()
     B = B.half().cuda().contiguous()
     D = torch.full((128, 64), float("nan"), device="cuda")
-    _lib.check(L.mems_selftest_umma(0, variant, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+    _lib.check_tools(_lib.tools_lib().mems_tools_selftest_umma(0, variant, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
                                     ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "selftest")
     torch.cuda.synchronize()
     return D.double().cpu()
