@@ -6,6 +6,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 
@@ -30,18 +31,22 @@
 
 namespace {
 
-// CTA organisation: two independent worker groups; each owns one batch of chains at a time, two TMEM
-// tile slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and its own MMA
-// issuer warp.  Groups never synchronise with each other, so one group's accept/reject section
-// overlaps the other group's tensor work.
+// CTA organisation (round 2): 32 worker warps and nobody else.
+//   group  (2 per CTA, 16 warps)  owns one batch of chains at a time: proposals, accept/reject, adaptation;
+//   team   (2 per group, 8 warps) owns one TMEM tile slot (64 accumulator + 64 operand columns) and evaluates every
+//          second tile of the group's pass: 4 TMEM lane quarters (= warp % 4, a hardware rule) x 2 column halves.
+// Four independent teams keep the XU pipe (one exponential per activation) fed while other teams wait for their
+// accumulators or do per-tile / per-update bookkeeping; a team does not ping-pong between slots any more.  There is no
+// dedicated MMA-issuer warp: the last warp of a team to deliver its part of an A operand issues the team's MMAs
+// (team_arrive_issue), so all 1024 threads do epilogue work.  Groups never synchronise with each other.
+// Warp -> role: q = warp % 4, j = warp / 4: group = j % 2, team = (j / 2) % 2, column half = j / 4 -- groups alternate in
+// warp-id order because the warp scheduler prefers high warp ids.
 constexpr int NGROUP = 2;
-constexpr int GSLOT = 2;                       // tile slots per group
-// NH = worker warps per TMEM lane quarter: 1 -> a thread owns a whole 64-column row of the tile,
-// 2 -> two threads split the row (32 columns each), doubling the warps the scheduler can interleave.  Only NH = 2 is
-// instantiated (NH = 1 measured 30.8 M against 37.8 M chain-steps/s on the bench workload).
-__host__ __device__ constexpr int gthreads(int NH) { return 128 * NH; }                 // worker threads per group
-__host__ __device__ constexpr int nworker(int NH) { return NGROUP * gthreads(NH); }
-__host__ __device__ constexpr int nthreads(int NH) { return nworker(NH) + 32 * NGROUP; } // + one MMA issuer warp per group
+constexpr int GTEAM = 2;                       // teams (= tile slots) per group
+constexpr int NH = 2;                          // column halves: a thread owns 32 of the 64 accumulator columns of its row
+constexpr int TEAM_WARPS = 4 * NH;
+constexpr int GTHREADS = 32 * TEAM_WARPS * GTEAM;     // 512 threads per group
+constexpr int NTHREADS = NGROUP * GTHREADS;           // 1024
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -58,19 +63,24 @@ constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct GroupSmem {
     ChainBatch cb;
-    double Spart[128];
-    float xchg[GSLOT][128];            // NH=2: partial output-layer dot of the upper column half
-    unsigned long long bar_A[GSLOT];   // workers -> MMA issuer: A operand of the slot is in TMEM
-    unsigned long long bar_D[GSLOT];   // tensor core -> workers: accumulator of the slot is complete
-    unsigned long long bar_X[GSLOT][4]; // NH=2: upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
-    unsigned long long bar_S;          // workers -> MMA issuer: ctrl_tiles of the next pass is valid
-    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
+    double Spart[GTEAM][128];          // per team: partial sums of squared residuals of its rows
+    double Sdense[GTEAM][MEMS_NCMAX];  // dense passes: per team, per chain slot
+    double R2[GTEAM][128];             // dense passes: squared residual of every row of the team's current tile
+    float xchg[GTEAM][128];            // partial output-layer dot of the upper column half
+    unsigned long long bar_D[GTEAM];   // tensor core -> team: accumulator of the slot is complete
+    unsigned long long bar_X[GTEAM][4]; // upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
+    unsigned int arrive_cnt[GTEAM];    // warps of the team that delivered their part of the current A operand (mod 8)
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
-    float cact[2 * 8 * MEMS_WIDTH];    // scratch of the coarse (FFT surrogate) first stage of delayed acceptance
-    double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
 };
+// Scratch of the coarse (FFT surrogate) first stage of delayed acceptance: 2*(2*GTHREADS/64)*64 floats.  It lives in the
+// component-wise sampler's per-chain scale arrays of the batch (scale_cw, lambda_cw), which delayed acceptance never uses.
+constexpr int COARSE_SCRATCH_FLOATS = 2 * (2 * GTHREADS / 64) * MEMS_WIDTH;
+static_assert(offsetof(ChainBatch, lambda_cw) == offsetof(ChainBatch, scale_cw) + sizeof(double) * MEMS_PMAX * MEMS_NCMAX,
+              "scale_cw and lambda_cw must be adjacent");
+static_assert(sizeof(float) * COARSE_SCRATCH_FLOATS <= 2 * sizeof(double) * MEMS_PMAX * MEMS_NCMAX, "coarse scratch does not fit");
+__device__ __forceinline__ float* coarse_scratch(ChainBatch& cb) { return reinterpret_cast<float*>(&cb.scale_cw[0][0]); }
 
 struct TcSmem {
     __align__(1024) unsigned char wimg[NBLK * BLK];
