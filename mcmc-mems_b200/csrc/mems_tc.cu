@@ -13,9 +13,9 @@
 //             against [b_hi; b_mid; b_lo]; 2*log2(e) is folded into weights and biases on the host so the
 //             accumulator is directly the exp2 argument of tanh(z) = 1 - 2/(2^(2z*log2 e) + 1).
 //   layer 1   the (P+1)->64 layer is a K=32 MMA over three-way-split scaled inputs.
-//   pipeline  4 tiles in flight per SM (4 x 128 TMEM columns), one per team of 8 warps (mems_tc_device.cuh: two groups
-//             of two teams); the warp that completes a team's A operand issues the team's MMAs, so every warp of
-//             the CTA is an epilogue worker and the teams cover each other's accumulator waits.
+//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns) in two independent groups; per group eight
+//             hidden-layer warps, four tail warps (last tanh layer + output layer + residual + next tile's layer-1
+//             operand) and one MMA-issuer warp (mems_tc_device.cuh), handing a slot round by mbarriers.
 //   tail      64->1 output layer, residual against y_obs, squared-sum reduction in FP64, accept/reject
 //             and chain-state update (mems_common.cuh) all happen in the same kernel.
 //
@@ -52,58 +52,49 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// Who am I: see the CTA organisation in mems_tc_device.cuh.
-struct Role {
-    int g;      // group
-    int s;      // team of the group = TMEM tile slot
-    int h;      // column half
-    int q;      // TMEM lane quarter
-    int row;    // TMEM lane = row of the team's tile
-    int gt;     // thread index within the group, 0..GTHREADS-1 (gt < 128: team 0, column half 0)
-};
-__device__ __forceinline__ Role my_role() {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    Role r;
-    r.q = warp & 3;
-    const int j = warp >> 2;
-    r.g = j & 1;
-    const int gi = j >> 1;               // 0..3 within the group
-    r.s = gi & 1;
-    r.h = gi >> 1;
-    r.row = r.q * 32 + lane;
-    r.gt = gi * 128 + r.row;
-    return r;
-}
-
-__device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
-
-// Every thread of a team calls this when its part of the team's next A operand is in TMEM (tcgen05.st complete).
-// The warp whose arrival completes the operand (the eighth) issues the MMAs of `layer` on the team's slot and commits
-// them to the team's accumulator barrier.  The arrival counter only ever grows (no reset races): "eighth" = count % 8.
-__device__ __forceinline__ void team_arrive_issue(TcSmem& sm, GroupSmem& gs, const Role& me, int layer) {
-    tc_fence_before();
-    __syncwarp();
-    uint32_t last = 0;
-    if ((threadIdx.x & 31) == 0) {
-        uint32_t old;
-        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;"
-                     : "=r"(old) : "r"(smem_u32(&gs.arrive_cnt[me.s])) : "memory");
-        last = ((old & (uint32_t)(TEAM_WARPS - 1)) == (uint32_t)(TEAM_WARPS - 1)) ? 1u : 0u;
-    }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (last) {                                               // warp-uniform
-        tc_fence_after();
-        const uint32_t slot = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)((me.g * GTEAM + me.s) * 128);
-        if (elect_one()) {
-            issue_layer(smem_u32(sm.wimg), slot, layer);
-            umma_commit(&gs.bar_D[me.s]);
+// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues): for every
+// surrogate pass the group announces (ctrl_tiles via bar_S) it serves the group's two slots in the fixed order
+// the epilogue warps produce them; ctrl_tiles < 0 ends the loop.  `g` must be warp-uniform.
+// Per tile: layer 0 waits for the tail warps' layer-1 operand, layers 1..5 for the hidden warps' A operands; the
+// accumulators of layers 0..4 go to the hidden warps (bar_Dh), the one of layer 5 to the tail warps (bar_Dt).
+__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
+    const uint32_t wimg = smem_u32(sm.wimg);
+    const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
+    uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S
+    for (;;) {
+        mbar_wait(&gs.bar_S, (ph >> 4) & 1u);
+        ph ^= 16u;
+        const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
+        if (n_tiles < 0) break;
+        const int n_pairs = (n_tiles + 1) >> 1;
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+#pragma unroll
+                for (int s = 0; s < GSLOT; ++s) {
+                    if (pair * 2 + s < n_tiles) {
+                        if (layer == 0) {
+                            mbar_wait(&gs.bar_At[s], (ph >> (2 + s)) & 1u);
+                            ph ^= (4u << s);
+                        } else {
+                            mbar_wait(&gs.bar_Ah[s], (ph >> s) & 1u);
+                            ph ^= (1u << s);
+                        }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            issue_layer(wimg, base + s * 128, layer);
+                            umma_commit(layer < MEMS_HIDDEN - 1 ? &gs.bar_Dh[s] : &gs.bar_Dt[s]);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
         }
-        __syncwarp();
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Worker side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
+// Epilogue side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
 // ------------------------------------------------------------------------------------------
 // K-slot of (term, input) in the layer-1 operand: terms 0..2 multiply W_hi, 3..4 multiply W_lo
 template <int P>
@@ -128,34 +119,76 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
     set_half<P>(a1, k1_slot<P>(4, i), m);
 }
 
-// The threads of one group evaluate one batch; team s takes tiles s, s + GTEAM, ...  Thread (row, h) of a team owns TMEM
-// lane `row` of the team's slot and columns [32 h, 32 h + 32) of it; row `row` of every tile is (chain slot row mod nce,
+__device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
+
+// The epilogue threads of group g evaluate one batch: gt < HTHREADS are the hidden-layer threads (row = gt % 128, column
+// half gt / 128), the rest the tail threads (row = gt - HTHREADS).  Row `row` of every tile is (chain slot row mod nce,
 // time sub-row row / nce).
 // compact: only the gs.nlive chains listed in gs.map take part (nce = gs.nlive): proposals outside the prior box and,
 // in the delayed-acceptance second stage, proposals the first stage did not promote cost nothing -- the tiles are
 // rebuilt from the live chains, so the pass shrinks with the promotion rate.  Result: gs.Sfin[chain].
 // DENSE (compact passes only): (time, chain) pairs are laid out back to back, row i of tile k is pair f = 128k + i
-// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A thread
-// then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2) and
-// thread c < n_live of the team adds the entries of chain slot c in time order (deterministic).
+// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A tail
+// thread then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2)
+// and tail thread c < n_live adds the entries of chain slot c in time order (deterministic).
 template <int P, bool DENSE>
-__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, const Role& me, const double* s_yobs,
+__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int gt, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
                                               bool compact, float* y_out, int c0, uint32_t& ph) {
-    constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
-    const int row = me.row, h = me.h, q = me.q, s = me.s, gt = me.gt;
+    const bool is_tail = gt >= HTHREADS;
+    const int row = is_tail ? gt - HTHREADS : (gt & 127);
+    const int q = row >> 5;
     const int nce = compact ? gs.nlive : nc;          // chains laid out in the tiles (any value in 1..128)
-    const int jc = row % nce;                         // rows >= nce*tpt of a tile idle
-    const int sub = row / nce;
     const int tpt = 128 / nce;                        // time points per tile
-    const int j = compact ? (int)gs.map[jc] : jc;     // batch-local chain index
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
     const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
-    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((me.g * GTEAM + s) * 128);
-    const bool chain_live = (sub < tpt) && (compact || jc < ncv);
+    const int n_pairs = (n_tiles + 1) >> 1;
+    const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
+    if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
+        *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
+        mbar_arrive(&gs.bar_S);
+    }
 
-    uint32_t a1[16];
-    if (h == 0) {
+    if (!is_tail) {
+        // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
+        constexpr int NCOL = 64 / NH;                 // accumulator columns per thread
+        const int h = gt >> 7;                        // column half
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int layer = 0; layer < MEMS_HIDDEN - 1; ++layer) {
+#pragma unroll
+                for (int s = 0; s < GSLOT; ++s) {
+                    if (pair * 2 + s < n_tiles) {
+                        const uint32_t tD = tD0 + s * 128;
+                        mbar_wait(&gs.bar_Dh[s], (ph >> s) & 1u);
+                        ph ^= (1u << s);
+                        tc_fence_after();
+                        // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain
+                        // than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
+                        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
+#pragma unroll
+                        for (int pc = 0; pc < NCOL / EC; ++pc) {
+                            uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
+                            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                            tc_wait_ld();
+                            epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
+                            tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
+                            tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
+                        }
+                        tc_wait_st();
+                        tc_fence_before();
+                        mbar_arrive(&gs.bar_Ah[s]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- tail warps: layer-1 operands, last tanh layer + output layer, residuals
+        const int jc = row % nce;                     // rows >= nce*tpt of a tile idle
+        const int sub = row / nce;
+        const int j = compact ? (int)gs.map[jc] : jc; // batch-local chain index
+        const bool chain_live = (sub < tpt) && (compact || jc < ncv);
+        uint32_t a1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
         if (!DENSE) {
@@ -165,71 +198,50 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, const R
         set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
         set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
         set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
-    }
-    // layer-1 operand of `tile` into the team's slot (column-half 0 threads)
-    auto stage_tile = [&](int tile) {
-        if (DENSE) {
-            const int f = tile * 128 + row;
-            const int ti = f / nce;
-            const bool ok = ti < Tn;
-            const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
+        // layer-1 operand of `tile` into slot s
+        auto stage_tile = [&](int s, int tile) {
+            if (DENSE) {
+                const int f = tile * 128 + row;
+                const int ti = f / nce;
+                const bool ok = ti < Tn;
+                const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
 #pragma unroll
-            for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
-            put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
-        } else {
-            const int ti = tile * tpt + sub;
-            put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
-        }
-        tmem_st16(tD + 64, a1);
-        tc_wait_st();
-    };
-
-    double Sp = 0.0;
-    for (int tile = s; tile < n_tiles; tile += GTEAM) {
-        if (h == 0) stage_tile(tile);
-        team_arrive_issue(sm, gs, me, 0);
-#pragma unroll 1
-        for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
-            mbar_wait(&gs.bar_D[s], ph & 1u);
-            ph ^= 1u;
-            tc_fence_after();
-            // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer
-            // grain than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
-            constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
-            if (layer < MEMS_HIDDEN - 1) {
-#pragma unroll
-                for (int pc = 0; pc < NCOL / EC; ++pc) {
-                    uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
-                    tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                    tc_wait_ld();
-                    epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
-                    tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
-                    tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
-                }
-                tc_wait_st();
-                team_arrive_issue(sm, gs, me, layer + 1);
+                for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
+                put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
             } else {
-                uint64_t acc = pk(0.0f, 0.0f);
+                const int ti = tile * tpt + sub;
+                put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
+            }
+            tmem_st16(tD0 + s * 128 + 64, a1);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&gs.bar_At[s]);
+        };
 #pragma unroll
-                for (int pc = 0; pc < NCOL / EC; ++pc) {
-                    uint32_t w[EC];
-                    tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                    tc_wait_ld();
+        for (int s = 0; s < GSLOT; ++s)
+            if (s < n_tiles) stage_tile(s, s);
+
+        double Sp = 0.0;
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int s = 0; s < GSLOT; ++s) {
+                const int tile = pair * 2 + s;
+                if (tile < n_tiles) {
+                    const uint32_t tD = tD0 + s * 128;
+                    mbar_wait(&gs.bar_Dt[s], (ph >> s) & 1u);
+                    ph ^= (1u << s);
+                    tc_fence_after();
+                    uint64_t acc = pk(0.0f, 0.0f);
 #pragma unroll
-                    for (int g8 = 0; g8 < EC / 8; ++g8)
-                        acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
-                }
-                float oa, ob;
-                upk(acc, oa, ob);
-                float o = oa + ob;
-                if (h == 1) {                              // the upper column half hands its partial dot to the lower one
-                    gs.xchg[s][row] = o;
-                    mbar_arrive(&gs.bar_X[s][q]);          // release: the store above is visible to the waiter
-                } else {
-                    mbar_wait(&gs.bar_X[s][q], (ph >> 1) & 1u);   // bit 1 of ph: bar_X parity
-                    ph ^= 2u;
-                    o += gs.xchg[s][row];
-                    o += sm.b7;
+                    for (int pc = 0; pc < 8; ++pc) {   // the whole row: tanh of the last hidden layer . output weights
+                        uint32_t w[8];
+                        tmem_ld8(tD + 8 * pc, w);
+                        tc_wait_ld();
+                        acc = epilogue_dot8(w, sm.w7 + 8 * pc, acc);
+                    }
+                    float oa, ob;
+                    upk(acc, oa, ob);
+                    const float o = oa + ob + sm.b7;
                     if (DENSE) {
                         const int f = tile * 128 + row;
                         const int ti = f / nce;
@@ -239,14 +251,13 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, const R
                             r2 = r * r;
                         }
                         gs.R2[s][row] = r2;
-                        named_bar_sync(3 + me.g * GTEAM + s, 128);     // the tile's 128 residuals are in shared memory
+                        named_bar_sync(3 + g, TTHREADS);               // the tile's 128 residuals are in shared memory
                         if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
                             int r0 = row - (tile * 128) % nce;
                             if (r0 < 0) r0 += nce;
                             for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
                         }
-                        // R2[s] is rewritten only after the team's next tile has gone through six accumulator barriers,
-                        // which every reader above has to pass as well
+                        // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
                     } else {
                         const int ti = tile * tpt + sub;
                         const int t = ti * stride;
@@ -256,25 +267,28 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, const R
                             Sp = fma(r, r, Sp);
                         }
                     }
+                    // this slot's D and A are free again: stage the layer-1 operand of its next tile
+                    const int nt = tile + GSLOT;
+                    if (nt < n_tiles) stage_tile(s, nt);
+                    else tc_fence_before();
                 }
-                tc_fence_before();                         // the slot's D and A are free again (next tile: stage + arrive)
             }
         }
+        if (DENSE) {
+            if (row < nce) gs.Sfin[gs.map[row]] = Sp; // tail thread `row` summed chain slot `row` over all tiles
+        } else {
+            gs.Spart[row] = Sp;
+        }
     }
-    if (DENSE) {
-        if (h == 0 && row < nce) gs.Sdense[s][row] = Sp;   // thread `row` of each team summed chain slot `row` over the team's tiles
-        group_bar_sync(me.g);
-        if (gt < nce) gs.Sfin[gs.map[gt]] = gs.Sdense[0][gt] + gs.Sdense[1][gt];
-    } else {
-        if (h == 0) gs.Spart[s][row] = Sp;
-        group_bar_sync(me.g);
+    if (!DENSE) {
+        group_bar_sync(g);
         if (gt < nce) {
-            double S = 0.0;                                // fixed order: time sub-rows ascending, teams inside
-            for (int u = 0; u < tpt; ++u) S += gs.Spart[0][u * nce + gt] + gs.Spart[1][u * nce + gt];
+            double S = 0.0;                            // fixed order: time sub-rows ascending
+            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
             gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
         }
     }
-    group_bar_sync(me.g);                                  // Sfin[chain] may have been written by another thread
+    group_bar_sync(g);                                 // Sfin[chain] may have been written by another thread
 }
 
 // Compaction of the chains that need the coming pass: gs.map / gs.nlive (first warp of the group; ballot prefix sums).
@@ -295,23 +309,39 @@ __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt,
     group_bar_sync(g);
 }
 
+// thread -> (group, index within the group's epilogue threads); issuer warps get gt = -1
+//   tid <  NGROUP*HTHREADS                : hidden threads, group = tid / HTHREADS, gt = tid % HTHREADS
+//   tid <  NWORKER                        : tail threads,   group = (tid - 512) / TTHREADS, gt = HTHREADS + row
+//   else                                  : MMA issuer warp of group (tid - NWORKER) / 32
+// (warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both worker kinds)
+__device__ __forceinline__ void my_role(int& g, int& gt) {
+    const int tid = threadIdx.x;
+    if (tid < NGROUP * HTHREADS) { g = tid / HTHREADS; gt = tid % HTHREADS; }
+    else if (tid < NWORKER) { g = (tid - NGROUP * HTHREADS) / TTHREADS; gt = HTHREADS + (tid - NGROUP * HTHREADS) % TTHREADS; }
+    else { g = (tid - NWORKER) >> 5; gt = -1; }
+}
+
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
 __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, double* s_yobs, float* s_ts) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     if (tid == 0) {
-        for (int g = 0; g < NGROUP; ++g)
-            for (int s = 0; s < GTEAM; ++s) {
-                mbar_init(&sm.grp[g].bar_D[s], 1);
-                for (int q = 0; q < 4; ++q) mbar_init(&sm.grp[g].bar_X[s][q], 32);
-                sm.grp[g].arrive_cnt[s] = 0u;
+        for (int g = 0; g < NGROUP; ++g) {
+            for (int s = 0; s < GSLOT; ++s) {
+                mbar_init(&sm.grp[g].bar_At[s], TTHREADS);
+                mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS);
+                mbar_init(&sm.grp[g].bar_Dh[s], 1);
+                mbar_init(&sm.grp[g].bar_Dt[s], 1);
             }
+            mbar_init(&sm.grp[g].bar_S, 1);
+            sm.grp[g].ctrl_tiles = 0;
+        }
         mbar_init(&sm.bar_w, 1);
         sm.c = pb.c;
         fence_barrier_init();
     }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == NWORKER / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&sm.tmem_base)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -332,7 +362,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
 __device__ __forceinline__ void tc_epilogue_free(TcSmem& sm) {
     tc_fence_before();
     __syncthreads();
-    if ((threadIdx.x >> 5) == 0) {
+    if ((threadIdx.x >> 5) == NWORKER / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(sm.tmem_base), "r"(512) : "memory");
     }
@@ -348,41 +378,52 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     tc_prologue(sm, pb, s_yobs, s_ts);
 
-    const Role me = my_role();
     const int T = sm.c.T, nc = ra.nc;
     const int nbatch = (ch.C + nc - 1) / nc;
-    const int g = me.g, gt = me.gt;
+    int g, gt;
+    my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
-    uint32_t ph = 0;
-    for (int batch = gid; batch < nbatch; batch += gstride) {
-        const int c0 = batch * nc;
-        const int ncv = min(nc, ch.C - c0);
-        group_bar_sync(g);
-        batch_load(gs.cb, ch, P, ra.mode, c0, gt, ncv);
-        for (int s = 0; s < ra.n_steps; ++s) {
-            for (int sub = 0; sub < ra.n_sub; ++sub) {
-                if (gt < ncv) batch_pre(gs.cb, sm.c, ch, ra, c0, gt, s, sub);
-                // only the chains that need this pass are laid out in tiles (proposals outside the prior box and
-                // proposals the DA first stage did not promote drop out); no live chain -> the pass is skipped
-                group_compact_live(gs, g, gt, ncv);
-                const bool any = gs.nlive > 0;
-                if (any && batch_pass_is_coarse_model(ra, sub))   // DA first stage on the FFT surrogate (FP32, CUDA cores)
-                    coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, coarse_scratch(gs.cb), gt, GTHREADS,
-                                    [g] { group_bar_sync(g); });
-                else if (any) {
-                    // dense packing when it saves tiles (n_live does not divide 128 well)
-                    const int stride = batch_pass_stride(ra, sub);
-                    const int Tn = (T + stride - 1) / stride, tpt = 128 / gs.nlive;
-                    if ((gs.nlive * Tn + 127) / 128 < (Tn + tpt - 1) / tpt)
-                        tc_eval_group<P, true>(sm, gs, me, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
-                    else
-                        tc_eval_group<P, false>(sm, gs, me, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
+
+    if (gt < 0) {
+        const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
+    } else {
+        uint32_t ph = 0;
+        for (int batch = gid; batch < nbatch; batch += gstride) {
+            const int c0 = batch * nc;
+            const int ncv = min(nc, ch.C - c0);
+            group_bar_sync(g);
+            batch_load(gs.cb, ch, P, ra.mode, c0, gt, ncv);
+            for (int s = 0; s < ra.n_steps; ++s) {
+                for (int sub = 0; sub < ra.n_sub; ++sub) {
+                    if (gt < ncv) batch_pre(gs.cb, sm.c, ch, ra, c0, gt, s, sub);
+                    // only the chains that need this pass are laid out in tiles (proposals outside the prior box and
+                    // proposals the DA first stage did not promote drop out); no live chain -> the pass is skipped
+                    group_compact_live(gs, g, gt, ncv);
+                    const bool any = gs.nlive > 0;
+                    if (any && batch_pass_is_coarse_model(ra, sub))   // DA first stage on the FFT surrogate (FP32, CUDA cores)
+                        coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, coarse_scratch(gs.cb), gt,
+                                        GTHREADS, [g] { group_bar_sync(g); });
+                    else if (any) {
+                        // dense packing when it saves tiles (n_live does not divide 128 well)
+                        const int stride = batch_pass_stride(ra, sub);
+                        const int Tn = (T + stride - 1) / stride, tpt = 128 / gs.nlive;
+                        if ((gs.nlive * Tn + 127) / 128 < (Tn + tpt - 1) / tpt)
+                            tc_eval_group<P, true>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
+                        else
+                            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
+                    }
+                    if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt] == 1) ? gs.Sfin[gt] : 0.0);
                 }
-                if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt] == 1) ? gs.Sfin[gt] : 0.0);
             }
+            batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
         }
-        batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
+        group_bar_sync(g);
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
+        }
     }
     tc_epilogue_free(sm);
 }
@@ -398,34 +439,45 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     tc_prologue(sm, pb, s_yobs, s_ts);
 
-    const Role me = my_role();
     const int T = sm.c.T;
     const int nbatch = (n + nc - 1) / nc;
-    const int g = me.g, gt = me.gt;
+    int g, gt;
+    my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
-    uint32_t ph = 0;
-    for (int batch = gid; batch < nbatch; batch += gstride) {
-        const int c0 = batch * nc;
-        const int ncv = min(nc, n - c0);
-        group_bar_sync(g);
-        if (gt < ncv) {
-            bool inb = true;
-            for (int p = 0; p < P; ++p) {
-                const double v = x[(size_t)p * n + c0 + gt];
-                gs.cb.xs[p][gt] = scale_param(sm.c, p, v);
-                inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
+
+    if (gt < 0) {
+        const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
+    } else {
+        uint32_t ph = 0;
+        for (int batch = gid; batch < nbatch; batch += gstride) {
+            const int c0 = batch * nc;
+            const int ncv = min(nc, n - c0);
+            group_bar_sync(g);
+            if (gt < ncv) {
+                bool inb = true;
+                for (int p = 0; p < P; ++p) {
+                    const double v = x[(size_t)p * n + c0 + gt];
+                    gs.cb.xs[p][gt] = scale_param(sm.c, p, v);
+                    inb = inb && !(v < sm.c.low[p]) && !(v > sm.c.high[p]);
+                }
+                gs.cb.inb[gt] = inb ? 1 : 0;
+                gs.cb.live[gt] = 1;
             }
-            gs.cb.inb[gt] = inb ? 1 : 0;
-            gs.cb.live[gt] = 1;
+            group_bar_sync(g);
+            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, ph);
+            if (gt < ncv && ll_out) {
+                // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
+                const int Tn = (T + stride - 1) / stride;
+                const double ll = sm.c.neg_half_inv_sigma2 * gs.Sfin[gt] * ((double)T / (double)Tn);
+                ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
+            }
         }
         group_bar_sync(g);
-        tc_eval_group<P, false>(sm, gs, me, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, ph);
-        if (gt < ncv && ll_out) {
-            // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
-            const int Tn = (T + stride - 1) / stride;
-            const double ll = sm.c.neg_half_inv_sigma2 * gs.Sfin[gt] * ((double)T / (double)Tn);
-            ll_out[c0 + gt] = (apply_prior && !gs.cb.inb[gt]) ? -CUDART_INF : ll;
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
         }
     }
     tc_epilogue_free(sm);

@@ -31,22 +31,26 @@
 
 namespace {
 
-// CTA organisation (round 2): 32 worker warps and nobody else.
-//   group  (2 per CTA, 16 warps)  owns one batch of chains at a time: proposals, accept/reject, adaptation;
-//   team   (2 per group, 8 warps) owns one TMEM tile slot (64 accumulator + 64 operand columns) and evaluates every
-//          second tile of the group's pass: 4 TMEM lane quarters (= warp % 4, a hardware rule) x 2 column halves.
-// Four independent teams keep the XU pipe (one exponential per activation) fed while other teams wait for their
-// accumulators or do per-tile / per-update bookkeeping; a team does not ping-pong between slots any more.  There is no
-// dedicated MMA-issuer warp: the last warp of a team to deliver its part of an A operand issues the team's MMAs
-// (team_arrive_issue), so all 1024 threads do epilogue work.  Groups never synchronise with each other.
-// Warp -> role: q = warp % 4, j = warp / 4: group = j % 2, team = (j / 2) % 2, column half = j / 4 -- groups alternate in
-// warp-id order because the warp scheduler prefers high warp ids.
+// CTA organisation (round 2): two independent groups per CTA; each owns one batch of chains at a time, two TMEM tile
+// slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and three kinds of warps:
+//   hidden warps (8 per group)  epilogue of the five hidden tanh layers: TMEM lane quarter = warp % 4 (a hardware rule),
+//                               column half = (warp / 4) % 2 -- a thread owns 32 of the 64 accumulator columns of its row;
+//   tail warps   (4 per group)  everything that happens once per tile: the last tanh layer fused with the 64 -> 1 output
+//                               layer (a thread owns a whole row), the residual against y_obs and its squared sum, and the
+//                               layer-1 operand of the slot's next tile.  In round 1 the hidden warps did this too, serially;
+//                               it was 22 % of their time (profiles/r02_*), and while they did it the XU pipe idled;
+//   MMA issuer   (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit.
+// Hand-offs are mbarriers (tail -> issuer -> hidden -> issuer ... -> tail); groups never synchronise with each other, so
+// one group's accept/reject section overlaps the other group's tensor work.  The first min(n_chains, 128) hidden
+// threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
 constexpr int NGROUP = 2;
-constexpr int GTEAM = 2;                       // teams (= tile slots) per group
-constexpr int NH = 2;                          // column halves: a thread owns 32 of the 64 accumulator columns of its row
-constexpr int TEAM_WARPS = 4 * NH;
-constexpr int GTHREADS = 32 * TEAM_WARPS * GTEAM;     // 512 threads per group
-constexpr int NTHREADS = NGROUP * GTHREADS;           // 1024
+constexpr int GSLOT = 2;                       // tile slots per group
+constexpr int NH = 2;                          // column halves of the hidden warps
+constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
+constexpr int TTHREADS = 128;                  // tail threads per group
+constexpr int GTHREADS = HTHREADS + TTHREADS;  // 384: the threads of a group that meet at group barriers
+constexpr int NWORKER = NGROUP * GTHREADS;     // 768
+constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group = 832
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -63,13 +67,14 @@ constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct GroupSmem {
     ChainBatch cb;
-    double Spart[GTEAM][128];          // per team: partial sums of squared residuals of its rows
-    double Sdense[GTEAM][MEMS_NCMAX];  // dense passes: per team, per chain slot
-    double R2[GTEAM][128];             // dense passes: squared residual of every row of the team's current tile
-    float xchg[GTEAM][128];            // partial output-layer dot of the upper column half
-    unsigned long long bar_D[GTEAM];   // tensor core -> team: accumulator of the slot is complete
-    unsigned long long bar_X[GTEAM][4]; // upper-half warp of a lane quarter -> lower-half warp (partial dot ready)
-    unsigned int arrive_cnt[GTEAM];    // warps of the team that delivered their part of the current A operand (mod 8)
+    double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (tail threads)
+    double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
+    unsigned long long bar_At[GSLOT];  // tail -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
+    unsigned long long bar_Ah[GSLOT];  // hidden -> MMA issuer: A operand of the slot's next layer is in TMEM
+    unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of a hidden layer is complete
+    unsigned long long bar_Dt[GSLOT];  // tensor core -> tail warps: accumulator of the last tanh layer is complete
+    unsigned long long bar_S;          // group -> MMA issuer: ctrl_tiles of the next pass is valid
+    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
@@ -77,6 +82,7 @@ struct GroupSmem {
 // Scratch of the coarse (FFT surrogate) first stage of delayed acceptance: 2*(2*GTHREADS/64)*64 floats.  It lives in the
 // component-wise sampler's per-chain scale arrays of the batch (scale_cw, lambda_cw), which delayed acceptance never uses.
 constexpr int COARSE_SCRATCH_FLOATS = 2 * (2 * GTHREADS / 64) * MEMS_WIDTH;
+static_assert(GTHREADS % 64 == 0, "coarse_fft_pass needs a multiple of 64 threads");
 static_assert(offsetof(ChainBatch, lambda_cw) == offsetof(ChainBatch, scale_cw) + sizeof(double) * MEMS_PMAX * MEMS_NCMAX,
               "scale_cw and lambda_cw must be adjacent");
 static_assert(sizeof(float) * COARSE_SCRATCH_FLOATS <= 2 * sizeof(double) * MEMS_PMAX * MEMS_NCMAX, "coarse scratch does not fit");
