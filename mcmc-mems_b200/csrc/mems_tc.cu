@@ -231,16 +231,24 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     mbar_wait(&gs.bar_Dt[s], (ph >> s) & 1u);
                     ph ^= (1u << s);
                     tc_fence_after();
-                    uint64_t acc = pk(0.0f, 0.0f);
+                    // the whole row: tanh of the last hidden layer . output weights, MEMS_TAIL_COLS columns at a time as
+                    // independent groups of eight (the tail is on the critical path of the slot: latency matters here)
+                    uint64_t acc[MEMS_TAIL_COLS / 8];
 #pragma unroll
-                    for (int pc = 0; pc < 8; ++pc) {   // the whole row: tanh of the last hidden layer . output weights
-                        uint32_t w[8];
-                        tmem_ld8(tD + 8 * pc, w);
+                    for (int u = 0; u < MEMS_TAIL_COLS / 8; ++u) acc[u] = pk(0.0f, 0.0f);
+#pragma unroll
+                    for (int pc = 0; pc < 64 / MEMS_TAIL_COLS; ++pc) {
+                        uint32_t w[MEMS_TAIL_COLS];
+                        tmem_ld_n<MEMS_TAIL_COLS>(tD + MEMS_TAIL_COLS * pc, w);
                         tc_wait_ld();
-                        acc = epilogue_dot8(w, sm.w7 + 8 * pc, acc);
+#pragma unroll
+                        for (int u = 0; u < MEMS_TAIL_COLS / 8; ++u)
+                            acc[u] = epilogue_dot8(w + 8 * u, sm.w7 + MEMS_TAIL_COLS * pc + 8 * u, acc[u]);
                     }
+#pragma unroll
+                    for (int u = 1; u < MEMS_TAIL_COLS / 8; ++u) acc[0] = add2(acc[0], acc[u]);
                     float oa, ob;
-                    upk(acc, oa, ob);
+                    upk(acc[0], oa, ob);
                     const float o = oa + ob + sm.b7;
                     if (DENSE) {
                         const int f = tile * 128 + row;

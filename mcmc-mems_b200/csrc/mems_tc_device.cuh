@@ -22,6 +22,9 @@
 #ifndef MEMS_EPI_COLS
 #define MEMS_EPI_COLS 8        // accumulator columns a thread loads, transforms and stores at a time: 8, 16 or 32
 #endif
+#ifndef MEMS_TAIL_COLS
+#define MEMS_TAIL_COLS 16      // accumulator columns a tail thread loads and transforms at a time: 8, 16 or 32
+#endif
 #ifndef MEMS_EPI_R16
 #define MEMS_EPI_R16 0         // 1: one reciprocal per sixteen activations (needs MEMS_EPI_COLS >= 16)
 #endif

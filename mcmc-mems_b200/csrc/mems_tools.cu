@@ -715,6 +715,99 @@ umma_selftest_kernel(int variant, const __half* __restrict__ A, const __half* __
     }
 }
 
+// Epilogue + tensor core together (round 2): 16 epilogue warps run the mode-53 body (four 8-column pieces per 32 columns,
+// round-2 arithmetic) on the four 128-column slots while warp 16 issues the product kernel's MMA batches (12 TS-form
+// + 1 SS-form tcgen05.mma, N = 64) on the same slots: `duty` = 0 no MMAs, 1 one batch then a pause of ~2 batch times
+// (the product kernel's tensor duty), 2 back to back.  Tells whether tensor-core TMEM / shared-memory traffic slows the
+// epilogue down.  cycles_out[blk] = slowest epilogue thread.
+__global__ void __launch_bounds__(544, 1)
+epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* sB = smem_raw;                    // B (8 KB) + A of the SS-form MMA (16 KB), zero
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 3 * BLK);
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(smem_raw + 3 * BLK + 16);
+    volatile int* stop = reinterpret_cast<volatile int*>(smem_raw + 3 * BLK + 32);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 3 * BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    if (tid == 0) { mbar_init(bar, 1); *stop = 0; fence_barrier_init(); }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tbase)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = *tbase;
+    __shared__ long long tmax;
+    if (tid == 0) tmax = 0;
+    uint32_t acc = 0;
+    if (warp < 16) {
+        const uint32_t tl = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0x3c003c00u;
+        tmem_st16(tl, z); tmem_st16(tl + 16, z); tmem_st16(tl + 32, z); tmem_st16(tl + 48, z);
+        tmem_st16(tl + 64, z); tmem_st16(tl + 80, z); tmem_st16(tl + 96, z); tmem_st16(tl + 112, z);
+        tc_wait_st();
+        tc_fence_before();
+        named_bar_sync(1, 544);
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            uint32_t w[8], h4[4], l4[4];
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+                tmem_ld8(tl + 8 * q8 + 32 * (it & 1), w);
+                tc_wait_ld();
+                epilogue_split_v2<1>(w, h4, l4);
+                tmem_st4(tl + 64 + 4 * q8 + 16 * (it & 1), h4);
+                tmem_st4(tl + 96 + 4 * q8 + 16 * (it & 1), l4);
+                acc ^= h4[0];
+            }
+            tc_wait_st();
+        }
+        const long long t1 = clock64();
+        atomicMax(reinterpret_cast<unsigned long long*>(&tmax), (unsigned long long)(t1 - t0));
+        tc_fence_before();
+        named_bar_sync(2, 512);
+        if (tid == 0) *stop = 1;
+    } else {
+        named_bar_sync(1, 544);
+        tc_fence_after();
+        const uint64_t b = make_desc(smem_u32(sB));
+        const uint64_t a = make_desc(smem_u32(sB + BLK));
+        uint32_t par = 0;
+        int slot = 0;
+        while (duty > 0 && !*stop) {
+            const uint32_t d = base + (uint32_t)(slot * 128);
+            if (elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, b + 2 * ks, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, b + 2 * ks, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, b + 2 * ks, 1u);
+                umma_ss(d, a, b, 1u);
+                umma_commit(bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, par);
+            par ^= 1u;
+            slot = (slot + 1) & 3;
+            if (duty == 1) { const long long until = clock64() + 1100; while (clock64() < until) {} }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+    if (tid == 0) cycles_out[blockIdx.x] = tmax;
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512) : "memory");
+    }
+}
+
 }  // namespace
 
 static int microbench_launch(int mode, int warps, int iters, int blocks, long long* cycles_out, unsigned int* sink, cudaStream_t st) {
@@ -738,6 +831,11 @@ static int microbench_launch(int mode, int warps, int iters, int blocks, long lo
 #define MB_CASE(M) case M: microbench_kernel<M><<<blocks, 32 * warps, 0, st>>>(iters, cycles_out, sink); break;
         MB_CASE(50) MB_CASE(51) MB_CASE(52) MB_CASE(53) MB_CASE(60) MB_CASE(61) MB_CASE(62) MB_CASE(63) MB_CASE(64) MB_CASE(65) MB_CASE(66) MB_CASE(67) MB_CASE(68)
 #undef MB_CASE
+        case 200: case 201: case 202: {          // epilogue (16 warps) + MMA stream: duty = mode - 200
+            const size_t smem = 3 * BLK + 64;
+            epi_mma_kernel<<<blocks, 544, smem, st>>>(mode - 200, iters, cycles_out, sink);
+            break;
+        }
         case 100: case 101: {          // MMA rate probe: `warps` carries N/8 (8, 16 or 32), mode 100 = A in TMEM, 101 = A in smem
             const size_t smem = 6 * BLK + 64;
             cudaError_t e = cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
