@@ -47,7 +47,7 @@ extern "C" {
 typedef struct MemsConfig {
     int32_t n_params;   /* P: sampled parameters = surrogate inputs minus the time column */
     int32_t n_time;     /* T: time points per signal (len(data_processor.time)); y_obs and the
-                           time column live in shared memory: T <= 2302 on the tensor-core
+                           time column live in shared memory: T <= 1961 on the tensor-core
                            path, 3621 on the FP32 path (mems_create reports the limit)      */
     int32_t n_chains;   /* C: independent chains resident on this device                  */
     int32_t path;       /* MEMS_PATH_FP32 or MEMS_PATH_TC                                 */

@@ -13,9 +13,9 @@
 //             against [b_hi; b_mid; b_lo]; 2*log2(e) is folded into weights and biases on the host so the
 //             accumulator is directly the exp2 argument of tanh(z) = 1 - 2/(2^(2z*log2 e) + 1).
 //   layer 1   the (P+1)->64 layer is a K=32 MMA over three-way-split scaled inputs.
-//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns) in two independent groups; per group eight
-//             hidden-layer warps, four tail warps (last tanh layer + output layer + residual + next tile's layer-1
-//             operand) and one MMA-issuer warp (mems_tc_device.cuh), handing a slot round by mbarriers.
+//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns), two per group of chains; sixteen stateless server
+//             warps run the epilogue of whichever slot has an accumulator ready, four control warps per group do the
+//             per-tile and per-update work, one warp per group issues the MMAs (mems_tc_device.cuh).
 //   tail      64->1 output layer, residual against y_obs, squared-sum reduction in FP64, accept/reject
 //             and chain-state update (mems_common.cuh) all happen in the same kernel.
 //
@@ -52,11 +52,19 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues): for every
-// surrogate pass the group announces (ctrl_tiles via bar_S) it serves the group's two slots in the fixed order
-// the epilogue warps produce them; ctrl_tiles < 0 ends the loop.  `g` must be warp-uniform.
-// Per tile: layer 0 waits for the tail warps' layer-1 operand, layers 1..5 for the hidden warps' A operands; the
-// accumulators of layers 0..4 go to the hidden warps (bar_Dh), the one of layer 5 to the tail warps (bar_Dt).
+#ifndef MEMS_POLL_SLEEP
+#define MEMS_POLL_SLEEP 0          // nanoseconds an idle polling warp sleeps between scans (0 = spin)
+#endif
+__device__ __forceinline__ void poll_pause() {
+#if MEMS_POLL_SLEEP > 0
+    __nanosleep(MEMS_POLL_SLEEP);
+#endif
+}
+
+// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues).  For every surrogate
+// pass the control warps announce (ctrl_tiles via bar_S) it serves the group's two slots in whatever order their A
+// operands complete: layer 0 of a tile waits for the control warps' layer-1 operand (bar_At), layers 1..5 for the
+// server warps' A operands (bar_Ah); every accumulator is committed to the slot's bar_D.  ctrl_tiles < 0 ends the loop.
 __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
@@ -66,35 +74,124 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
         ph ^= 16u;
         const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
         if (n_tiles < 0) break;
-        const int n_pairs = (n_tiles + 1) >> 1;
-        for (int pair = 0; pair < n_pairs; ++pair) {
-#pragma unroll 1
-            for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+        int left[GSLOT], layer[GSLOT];          // tiles the slot still has to start / finish, next layer to issue
 #pragma unroll
-                for (int s = 0; s < GSLOT; ++s) {
-                    if (pair * 2 + s < n_tiles) {
-                        if (layer == 0) {
-                            mbar_wait(&gs.bar_At[s], (ph >> (2 + s)) & 1u);
-                            ph ^= (4u << s);
-                        } else {
-                            mbar_wait(&gs.bar_Ah[s], (ph >> s) & 1u);
-                            ph ^= (1u << s);
-                        }
+        for (int s = 0; s < GSLOT; ++s) { left[s] = (n_tiles - s + GSLOT - 1) / GSLOT; layer[s] = 0; }
+        while (left[0] > 0 || left[1] > 0) {
+            bool any = false;
+#pragma unroll
+            for (int s = 0; s < GSLOT; ++s) {
+                if (left[s] > 0) {
+                    void* bar = (layer[s] == 0) ? (void*)&gs.bar_At[s] : (void*)&gs.bar_Ah[s];
+                    const uint32_t bit = (layer[s] == 0) ? (4u << s) : (1u << s);
+                    uint32_t ok = 0;
+                    if ((threadIdx.x & 31) == 0) ok = mbar_test(bar, (ph & bit) ? 1u : 0u) ? 1u : 0u;
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (ok) {
+                        mbar_wait(bar, (ph & bit) ? 1u : 0u);      // every lane observes the completed phase (returns at once)
+                        ph ^= bit;
                         tc_fence_after();
                         if (elect_one()) {
-                            issue_layer(wimg, base + s * 128, layer);
-                            umma_commit(layer < MEMS_HIDDEN - 1 ? &gs.bar_Dh[s] : &gs.bar_Dt[s]);
+                            issue_layer(wimg, base + s * 128, layer[s]);
+                            umma_commit(&gs.bar_D[s]);
                         }
                         __syncwarp();
+                        if (++layer[s] == MEMS_HIDDEN) { layer[s] = 0; --left[s]; }
+                        any = true;
                     }
                 }
             }
+            if (!any) poll_pause();          // (a protocol bug traps in the control warps' mbarrier watchdog)
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Epilogue side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
+// Server warps: the epilogue of any slot
+// ------------------------------------------------------------------------------------------
+// One item = one finished accumulator (slot, layer).  Hidden layers: accumulator -> tanh -> fp16 hi/lo split -> the
+// slot's next A operand (TMEM), then tell the slot's issuer.  Last tanh layer: fused with the 64 -> 1 output layer; the
+// partial dot of the thread's 32 columns goes to shared memory for the slot's control warps.
+__device__ __forceinline__ void server_item(TcSmem& sm, GroupSmem& gs, int sl, int layer, int q, int h, int row) {
+    constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
+    // the thread's columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain than the whole row keeps XU, FMA
+    // and ALU work of one warp interleaved: profiles/r02_microbench_*)
+    constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
+    const int s = sl & (GSLOT - 1);
+    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 128);
+    if (layer < MEMS_HIDDEN - 1) {
+#pragma unroll
+        for (int pc = 0; pc < NCOL / EC; ++pc) {
+            uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
+            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+            tc_wait_ld();
+            epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
+            tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
+            tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&gs.bar_Ah[s]);
+    } else {
+        uint64_t acc = pk(0.0f, 0.0f);
+#pragma unroll
+        for (int pc = 0; pc < NCOL / EC; ++pc) {
+            uint32_t w[EC];
+            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+            tc_wait_ld();
+#pragma unroll
+            for (int g8 = 0; g8 < EC / 8; ++g8)
+                acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
+        }
+        float oa, ob;
+        upk(acc, oa, ob);
+        gs.xchg[s][h][row] = oa + ob;
+        tc_fence_before();                                 // the accumulator has been read: the slot may be restaged
+        mbar_arrive(&gs.bar_T[s]);                         // release: the store above is visible to the control warps
+    }
+}
+
+__device__ __forceinline__ void server_loop(TcSmem& sm) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, h = (warp >> 2) & 1, role = warp & (NROLE - 1);
+    const int row = q * 32 + lane;
+    int rot = (warp >> 3) * GSLOT;                         // the two servers of a role start on different groups
+    for (;;) {
+        int found = -1;
+        uint32_t seq = 0;
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NSLOT; ++k) {
+                if (found < 0) {
+                    const int sl = (rot + k) & (NSLOT - 1);
+                    GroupSmem& gs = sm.grp[sl / GSLOT];
+                    const int s = sl & (GSLOT - 1);
+                    const uint32_t sq = *reinterpret_cast<volatile unsigned int*>(&gs.next[s][role]);
+                    if (mbar_test(&gs.bar_D[s], sq & 1u) && atomicCAS(&gs.next[s][role], sq, sq + 1u) == sq) {
+                        found = sl;
+                        seq = sq;
+                    }
+                }
+            }
+            if (found < 0 && *reinterpret_cast<volatile unsigned int*>(&sm.done) == (1u << NGROUP) - 1u) found = -2;
+        }
+        found = __shfl_sync(0xffffffffu, found, 0);
+        if (found == -2) break;
+        if (found < 0) {                                           // idling is legitimate (e.g. passes on the coarse model only)
+            poll_pause();
+            continue;
+        }
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        GroupSmem& gs = sm.grp[found / GSLOT];
+        mbar_wait(&gs.bar_D[found & (GSLOT - 1)], seq & 1u);       // every lane observes the completed phase (returns at once)
+        tc_fence_after();
+        server_item(sm, gs, found, (int)(seq % (uint32_t)ITEMS_PER_TILE), q, h, row);
+        rot = found + 1;                                           // look at the other slots first next time
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Control warps: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
 // ------------------------------------------------------------------------------------------
 // K-slot of (term, input) in the layer-1 operand: terms 0..2 multiply W_hi, 3..4 multiply W_lo
 template <int P>
@@ -121,22 +218,20 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
 
 __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
 
-// The epilogue threads of group g evaluate one batch: gt < HTHREADS are the hidden-layer threads (row = gt % 128, column
-// half gt / 128), the rest the tail threads (row = gt - HTHREADS).  Row `row` of every tile is (chain slot row mod nce,
-// time sub-row row / nce).
+// The 128 control threads of group g drive one surrogate pass over the group's batch: thread `row` owns row `row` of every
+// tile = (chain slot row mod nce, time sub-row row / nce).  They stage the layer-1 operands, the server warps and the
+// issuer do the six tanh layers, and the control threads turn the partial output-layer dots into residuals.
 // compact: only the gs.nlive chains listed in gs.map take part (nce = gs.nlive): proposals outside the prior box and,
 // in the delayed-acceptance second stage, proposals the first stage did not promote cost nothing -- the tiles are
 // rebuilt from the live chains, so the pass shrinks with the promotion rate.  Result: gs.Sfin[chain].
 // DENSE (compact passes only): (time, chain) pairs are laid out back to back, row i of tile k is pair f = 128k + i
-// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A tail
-// thread then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2)
-// and tail thread c < n_live adds the entries of chain slot c in time order (deterministic).
+// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A thread
+// then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2) and
+// thread c < n_live adds the entries of chain slot c in time order (deterministic).
 template <int P, bool DENSE>
-__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int gt, const double* s_yobs,
+__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int row, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
                                               bool compact, float* y_out, int c0, uint32_t& ph) {
-    const bool is_tail = gt >= HTHREADS;
-    const int row = is_tail ? gt - HTHREADS : (gt & 127);
     const int q = row >> 5;
     const int nce = compact ? gs.nlive : nc;          // chains laid out in the tiles (any value in 1..128)
     const int tpt = 128 / nce;                        // time points per tile
@@ -144,156 +239,97 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
-    if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
+    if (row == 0) {                                   // tell the group's MMA issuer how many tiles follow
         *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
         mbar_arrive(&gs.bar_S);
     }
-
-    if (!is_tail) {
-        // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
-        constexpr int NCOL = 64 / NH;                 // accumulator columns per thread
-        const int h = gt >> 7;                        // column half
-        for (int pair = 0; pair < n_pairs; ++pair) {
-#pragma unroll 1
-            for (int layer = 0; layer < MEMS_HIDDEN - 1; ++layer) {
+    const int jc = row % nce;                         // rows >= nce*tpt of a tile idle
+    const int sub = row / nce;
+    const int j = compact ? (int)gs.map[jc] : jc;     // batch-local chain index
+    const bool chain_live = (sub < tpt) && (compact || jc < ncv);
+    uint32_t a1[16];
 #pragma unroll
-                for (int s = 0; s < GSLOT; ++s) {
-                    if (pair * 2 + s < n_tiles) {
-                        const uint32_t tD = tD0 + s * 128;
-                        mbar_wait(&gs.bar_Dh[s], (ph >> s) & 1u);
-                        ph ^= (1u << s);
-                        tc_fence_after();
-                        // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain
-                        // than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
-                        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
+    for (int i = 0; i < 16; ++i) a1[i] = 0u;
+    if (!DENSE) {
 #pragma unroll
-                        for (int pc = 0; pc < NCOL / EC; ++pc) {
-                            uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
-                            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                            tc_wait_ld();
-                            epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
-                            tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
-                            tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
-                        }
-                        tc_wait_st();
-                        tc_fence_before();
-                        mbar_arrive(&gs.bar_Ah[s]);
-                    }
-                }
-            }
-        }
-    } else {
-        // ---- tail warps: layer-1 operands, last tanh layer + output layer, residuals
-        const int jc = row % nce;                     // rows >= nce*tpt of a tile idle
-        const int sub = row / nce;
-        const int j = compact ? (int)gs.map[jc] : jc; // batch-local chain index
-        const bool chain_live = (sub < tpt) && (compact || jc < ncv);
-        uint32_t a1[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) a1[i] = 0u;
-        if (!DENSE) {
-#pragma unroll
-            for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
-        }
-        set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
-        set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
-        set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
-        // layer-1 operand of `tile` into slot s
-        auto stage_tile = [&](int s, int tile) {
-            if (DENSE) {
-                const int f = tile * 128 + row;
-                const int ti = f / nce;
-                const bool ok = ti < Tn;
-                const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
-#pragma unroll
-                for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
-                put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
-            } else {
-                const int ti = tile * tpt + sub;
-                put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
-            }
-            tmem_st16(tD0 + s * 128 + 64, a1);
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(&gs.bar_At[s]);
-        };
-#pragma unroll
-        for (int s = 0; s < GSLOT; ++s)
-            if (s < n_tiles) stage_tile(s, s);
-
-        double Sp = 0.0;
-        for (int pair = 0; pair < n_pairs; ++pair) {
-#pragma unroll 1
-            for (int s = 0; s < GSLOT; ++s) {
-                const int tile = pair * 2 + s;
-                if (tile < n_tiles) {
-                    const uint32_t tD = tD0 + s * 128;
-                    mbar_wait(&gs.bar_Dt[s], (ph >> s) & 1u);
-                    ph ^= (1u << s);
-                    tc_fence_after();
-                    // the whole row: tanh of the last hidden layer . output weights, MEMS_TAIL_COLS columns at a time as
-                    // independent groups of eight (the tail is on the critical path of the slot: latency matters here)
-                    uint64_t acc[MEMS_TAIL_COLS / 8];
-#pragma unroll
-                    for (int u = 0; u < MEMS_TAIL_COLS / 8; ++u) acc[u] = pk(0.0f, 0.0f);
-#pragma unroll
-                    for (int pc = 0; pc < 64 / MEMS_TAIL_COLS; ++pc) {
-                        uint32_t w[MEMS_TAIL_COLS];
-                        tmem_ld_n<MEMS_TAIL_COLS>(tD + MEMS_TAIL_COLS * pc, w);
-                        tc_wait_ld();
-#pragma unroll
-                        for (int u = 0; u < MEMS_TAIL_COLS / 8; ++u)
-                            acc[u] = epilogue_dot8(w + 8 * u, sm.w7 + MEMS_TAIL_COLS * pc + 8 * u, acc[u]);
-                    }
-#pragma unroll
-                    for (int u = 1; u < MEMS_TAIL_COLS / 8; ++u) acc[0] = add2(acc[0], acc[u]);
-                    float oa, ob;
-                    upk(acc[0], oa, ob);
-                    const float o = oa + ob + sm.b7;
-                    if (DENSE) {
-                        const int f = tile * 128 + row;
-                        const int ti = f / nce;
-                        double r2 = 0.0;
-                        if (ti < Tn) {
-                            const double r = s_yobs[ti * stride] - (double)o;
-                            r2 = r * r;
-                        }
-                        gs.R2[s][row] = r2;
-                        named_bar_sync(3 + g, TTHREADS);               // the tile's 128 residuals are in shared memory
-                        if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
-                            int r0 = row - (tile * 128) % nce;
-                            if (r0 < 0) r0 += nce;
-                            for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
-                        }
-                        // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
-                    } else {
-                        const int ti = tile * tpt + sub;
-                        const int t = ti * stride;
-                        if (chain_live && ti < Tn) {
-                            if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
-                            const double r = s_yobs[t] - (double)o;
-                            Sp = fma(r, r, Sp);
-                        }
-                    }
-                    // this slot's D and A are free again: stage the layer-1 operand of its next tile
-                    const int nt = tile + GSLOT;
-                    if (nt < n_tiles) stage_tile(s, nt);
-                    else tc_fence_before();
-                }
-            }
-        }
+        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
+    }
+    set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);           // ones that pick up b_hi, b_mid, b_lo
+    set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
+    set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
+    // layer-1 operand of `tile` into slot s
+    auto stage_tile = [&](int s, int tile) {
         if (DENSE) {
-            if (row < nce) gs.Sfin[gs.map[row]] = Sp; // tail thread `row` summed chain slot `row` over all tiles
+            const int f = tile * 128 + row;
+            const int ti = f / nce;
+            const bool ok = ti < Tn;
+            const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
+            put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
         } else {
-            gs.Spart[row] = Sp;
+            const int ti = tile * tpt + sub;
+            put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
+        }
+        tmem_st16(tD0 + s * 128 + 64, a1);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&gs.bar_At[s]);
+    };
+#pragma unroll
+    for (int s = 0; s < GSLOT; ++s)
+        if (s < n_tiles) stage_tile(s, s);
+
+    double Sp = 0.0;
+    for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+        for (int s = 0; s < GSLOT; ++s) {
+            const int tile = pair * 2 + s;
+            if (tile < n_tiles) {
+                mbar_wait(&gs.bar_T[s], (ph >> s) & 1u);
+                ph ^= (1u << s);
+                tc_fence_after();
+                const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + sm.b7;
+                if (DENSE) {
+                    const int f = tile * 128 + row;
+                    const int ti = f / nce;
+                    double r2 = 0.0;
+                    if (ti < Tn) {
+                        const double r = s_yobs[ti * stride] - (double)o;
+                        r2 = r * r;
+                    }
+                    gs.R2[s][row] = r2;
+                    group_bar_sync(g);                             // the tile's 128 residuals are in shared memory
+                    if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
+                        int r0 = row - (tile * 128) % nce;
+                        if (r0 < 0) r0 += nce;
+                        for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
+                    }
+                    // R2[s] is written again two tiles later, behind the barrier of all control threads on R2[1 - s]
+                } else {
+                    const int ti = tile * tpt + sub;
+                    const int t = ti * stride;
+                    if (chain_live && ti < Tn) {
+                        if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                        const double r = s_yobs[t] - (double)o;
+                        Sp = fma(r, r, Sp);
+                    }
+                }
+                // this slot's D and A are free again: stage the layer-1 operand of its next tile
+                const int nt = tile + GSLOT;
+                if (nt < n_tiles) stage_tile(s, nt);
+            }
         }
     }
-    if (!DENSE) {
+    if (DENSE) {
+        if (row < nce) gs.Sfin[gs.map[row]] = Sp;     // thread `row` summed chain slot `row` over all tiles
+    } else {
+        gs.Spart[row] = Sp;
         group_bar_sync(g);
-        if (gt < nce) {
+        if (row < nce) {
             double S = 0.0;                            // fixed order: time sub-rows ascending
-            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
-            gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
+            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + row];
+            gs.Sfin[compact ? (int)gs.map[row] : row] = S;
         }
     }
     group_bar_sync(g);                                 // Sfin[chain] may have been written by another thread
@@ -317,16 +353,16 @@ __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt,
     group_bar_sync(g);
 }
 
-// thread -> (group, index within the group's epilogue threads); issuer warps get gt = -1
-//   tid <  NGROUP*HTHREADS                : hidden threads, group = tid / HTHREADS, gt = tid % HTHREADS
-//   tid <  NWORKER                        : tail threads,   group = (tid - 512) / TTHREADS, gt = HTHREADS + row
-//   else                                  : MMA issuer warp of group (tid - NWORKER) / 32
-// (warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both worker kinds)
-__device__ __forceinline__ void my_role(int& g, int& gt) {
+// thread -> role:  tid < STHREADS: server warp (kind 0);  tid < NWORKER: control thread `row` of group g (kind 1);
+// else MMA issuer warp of group g (kind 2).  warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both
+// worker kinds.
+__device__ __forceinline__ int my_role(int& g, int& row) {
     const int tid = threadIdx.x;
-    if (tid < NGROUP * HTHREADS) { g = tid / HTHREADS; gt = tid % HTHREADS; }
-    else if (tid < NWORKER) { g = (tid - NGROUP * HTHREADS) / TTHREADS; gt = HTHREADS + (tid - NGROUP * HTHREADS) % TTHREADS; }
-    else { g = (tid - NWORKER) >> 5; gt = -1; }
+    if (tid < STHREADS) { g = 0; row = 0; return 0; }
+    if (tid < NWORKER) { g = (tid - STHREADS) / GTHREADS; row = (tid - STHREADS) % GTHREADS; return 1; }
+    g = (tid - NWORKER) >> 5;
+    row = 0;
+    return 2;
 }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
@@ -336,15 +372,17 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
     if (tid == 0) {
         for (int g = 0; g < NGROUP; ++g) {
             for (int s = 0; s < GSLOT; ++s) {
-                mbar_init(&sm.grp[g].bar_At[s], TTHREADS);
-                mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS);
-                mbar_init(&sm.grp[g].bar_Dh[s], 1);
-                mbar_init(&sm.grp[g].bar_Dt[s], 1);
+                mbar_init(&sm.grp[g].bar_At[s], GTHREADS);
+                mbar_init(&sm.grp[g].bar_Ah[s], 32 * NROLE);
+                mbar_init(&sm.grp[g].bar_T[s], 32 * NROLE);
+                mbar_init(&sm.grp[g].bar_D[s], 1);
+                for (int r = 0; r < NROLE; ++r) sm.grp[g].next[s][r] = 0u;
             }
             mbar_init(&sm.grp[g].bar_S, 1);
             sm.grp[g].ctrl_tiles = 0;
         }
         mbar_init(&sm.bar_w, 1);
+        sm.done = 0u;
         sm.c = pb.c;
         fence_barrier_init();
     }
@@ -389,11 +427,13 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     const int T = sm.c.T, nc = ra.nc;
     const int nbatch = (ch.C + nc - 1) / nc;
     int g, gt;
-    my_role(g, gt);
+    const int kind = my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (gt < 0) {
+    if (kind == 0) {
+        server_loop(sm);
+    } else if (kind == 2) {
         const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
         mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
@@ -431,6 +471,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
         if (gt == 0) {
             *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
             mbar_arrive(&gs.bar_S);
+            atomicOr(&sm.done, 1u << g);
         }
     }
     tc_epilogue_free(sm);
@@ -450,11 +491,13 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const int T = sm.c.T;
     const int nbatch = (n + nc - 1) / nc;
     int g, gt;
-    my_role(g, gt);
+    const int kind = my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (gt < 0) {
+    if (kind == 0) {
+        server_loop(sm);
+    } else if (kind == 2) {
         const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
         mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
@@ -486,6 +529,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
         if (gt == 0) {
             *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
             mbar_arrive(&gs.bar_S);
+            atomicOr(&sm.done, 1u << g);
         }
     }
     tc_epilogue_free(sm);

@@ -34,26 +34,33 @@
 
 namespace {
 
-// CTA organisation (round 2): two independent groups per CTA; each owns one batch of chains at a time, two TMEM tile
-// slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and three kinds of warps:
-//   hidden warps (8 per group)  epilogue of the five hidden tanh layers: TMEM lane quarter = warp % 4 (a hardware rule),
-//                               column half = (warp / 4) % 2 -- a thread owns 32 of the 64 accumulator columns of its row;
-//   tail warps   (4 per group)  everything that happens once per tile: the last tanh layer fused with the 64 -> 1 output
-//                               layer (a thread owns a whole row), the residual against y_obs and its squared sum, and the
-//                               layer-1 operand of the slot's next tile.  In round 1 the hidden warps did this too, serially;
-//                               it was 22 % of their time (profiles/r02_*), and while they did it the XU pipe idled;
-//   MMA issuer   (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit.
-// Hand-offs are mbarriers (tail -> issuer -> hidden -> issuer ... -> tail); groups never synchronise with each other, so
-// one group's accept/reject section overlaps the other group's tensor work.  The first min(n_chains, 128) hidden
-// threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
+// CTA organisation (round 2): two independent groups per CTA; each owns one batch of chains at a time and two TMEM tile
+// slots.  Three kinds of warps:
+//   server warps  (16 per CTA, shared by both groups)  the epilogue of every tanh layer of every tile of all four slots.
+//                 A server warp has a fixed ROLE (TMEM lane quarter = warp % 4 -- a hardware rule -- and column half
+//                 (warp / 4) % 2: a thread owns 32 of the 64 accumulator columns of its row) but no fixed slot: it
+//                 claims the next finished accumulator of ANY slot for its role (two warps per role compete through a
+//                 per-slot, per-role sequence counter).  Stateless, so a group that is busy with accept/reject or waits
+//                 for the tensor core never idles them -- measured in round 1/2: with warps tied to a group the XU
+//                 pipe (one exponential per activation) was busy 60 % of the time, against 78 % for the epilogue alone;
+//   control warps (4 per group)  the per-tile work (partial output-layer dots -> residual against y_obs -> squared sum,
+//                 layer-1 operand of the slot's next tile) and the per-chain Metropolis-Hastings bookkeeping between
+//                 passes (proposals, accept/reject, adaptation, thinned stores);
+//   MMA issuer    (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit for whichever of the
+//                 group's slots has its next A operand complete.
+// Hand-offs are mbarriers: control -> issuer (bar_At) -> tensor core -> servers (bar_D) -> issuer (bar_Ah) ... -> servers
+// -> control (bar_T).  Groups never synchronise with each other.
 constexpr int NGROUP = 2;
 constexpr int GSLOT = 2;                       // tile slots per group
-constexpr int NH = 2;                          // column halves of the hidden warps
-constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
-constexpr int TTHREADS = 128;                  // tail threads per group
-constexpr int GTHREADS = HTHREADS + TTHREADS;  // 384: the threads of a group that meet at group barriers
-constexpr int NWORKER = NGROUP * GTHREADS;     // 768
+constexpr int NSLOT = NGROUP * GSLOT;
+constexpr int NH = 2;                          // column halves of the server warps
+constexpr int NROLE = 4 * NH;                  // server roles (lane quarter, column half)
+constexpr int SERVERS_PER_ROLE = 2;
+constexpr int STHREADS = 32 * NROLE * SERVERS_PER_ROLE;   // 512 server threads
+constexpr int GTHREADS = 128;                  // control threads per group = rows of a tile
+constexpr int NWORKER = STHREADS + NGROUP * GTHREADS;     // 768
 constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group = 832
+constexpr int ITEMS_PER_TILE = MEMS_HIDDEN;    // accumulators a slot delivers per tile (one per tanh layer)
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -70,13 +77,15 @@ constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct GroupSmem {
     ChainBatch cb;
-    double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (tail threads)
+    double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (control threads)
     double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
-    unsigned long long bar_At[GSLOT];  // tail -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
-    unsigned long long bar_Ah[GSLOT];  // hidden -> MMA issuer: A operand of the slot's next layer is in TMEM
-    unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of a hidden layer is complete
-    unsigned long long bar_Dt[GSLOT];  // tensor core -> tail warps: accumulator of the last tanh layer is complete
-    unsigned long long bar_S;          // group -> MMA issuer: ctrl_tiles of the next pass is valid
+    float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves (servers -> control)
+    unsigned long long bar_At[GSLOT];  // control -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
+    unsigned long long bar_Ah[GSLOT];  // servers -> MMA issuer: A operand of the slot's next layer is in TMEM
+    unsigned long long bar_D[GSLOT];   // tensor core -> servers: an accumulator of the slot is complete (every layer)
+    unsigned long long bar_T[GSLOT];   // servers -> control: the partial output-layer dots of the slot's tile are in xchg
+    unsigned long long bar_S;          // control -> MMA issuer: ctrl_tiles of the next pass is valid
+    unsigned int next[GSLOT][NROLE];   // per role: accumulators of the slot already claimed by a server (a sequence number)
     int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
@@ -100,7 +109,7 @@ struct TcSmem {
     GroupSmem grp[NGROUP];
     unsigned long long bar_w;
     uint32_t tmem_base;
-    uint32_t pad2_;
+    unsigned int done;                 // bit g: group g has no more work (servers leave when all bits are set)
     // followed by: double yobs[T]; float ts[T];
 };
 
@@ -131,6 +140,16 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");   // hardware-suspended wait, wakes on completion
 #endif
+    return ok != 0;
+}
+// Non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
 // Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.

@@ -541,7 +541,7 @@ def test_trace_length_limit_is_reported_at_creation():
     pb["time"] = np.linspace(0.0, 1.49e-3, 3000)
     pb["y_obs"] = np.zeros(3000)
     with pytest.raises(MemsError, match="does not fit in shared memory"):
-        helpers.engine(pb, 4, 1)            # the tensor-core path holds up to 2302 points next to the resident weights
+        helpers.engine(pb, 4, 1)            # the tensor-core path holds up to 1961 points next to the resident weights
     eng = helpers.engine(pb, 4, 0)          # the FP32 check path holds up to 3621 points
     eng.close()
 
