@@ -209,6 +209,12 @@ int  mems_lsq(mems_handle_t h, const double* x0_dev, int32_t n, const double* yo
               double ftol, double* x_out_dev, double* cov_out_dev, double* cost_out_dev, int32_t* iters_out_dev,
               void* stream);
 
+/* Surrogate rows (chain, time point) the run launches of this handle have evaluated since mems_init_chains: the
+ * tensor-core path skips proposals outside the prior box and, in delayed acceptance, proposals the first stage did
+ * not promote, so this -- not chains x updates x T -- is the work behind a throughput figure (bench bookkeeping).
+ * rows: HOST pointer; synchronises the stream. */
+int  mems_rows_evaluated(mems_handle_t h, uint64_t* rows, void* stream);
+
 /* Number of kernel launches issued through this handle since creation (bench bookkeeping). */
 int64_t mems_launch_count(mems_handle_t h);
 

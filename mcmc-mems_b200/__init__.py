@@ -11,7 +11,7 @@ from .utils import (create_forward_model_function, least_squares_optimization,  
                     objective_function, surrogate_spec, batched_least_squares, sensitivity_push_forward)
 from .cuqi_compat import (Gaussian, Uniform, JointDistribution, Posterior, Model, MH, CWMH,  # noqa: F401
                           DelayedAcceptanceMH, Samples, BatchedSamples, Continuous1D, Discrete)
-from . import diagnostics, diagnostics_device, distributed, h5lite  # noqa: F401
+from . import diagnostics, diagnostics_device, distributed, fixtures, h5lite  # noqa: F401
 
 __all__ = [
     "MHEngine", "SurrogateSpec", "NN_Model", "preprocessing", "FixtureProcessor",

@@ -192,7 +192,8 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
               cudaMalloc(&h->chains.lambda_cw, sizeof(double) * P * C) == cudaSuccess &&
               cudaMalloc(&h->chains.win_cw, sizeof(int) * P * C) == cudaSuccess &&
               cudaMalloc(&h->chains.llc, sizeof(double) * C) == cudaSuccess &&
-              cudaMalloc(&h->chains.prom_count, sizeof(unsigned int) * C) == cudaSuccess;
+              cudaMalloc(&h->chains.prom_count, sizeof(unsigned int) * C) == cudaSuccess &&
+              cudaMalloc(&h->chains.rows_eval, sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) {
         const char* msg = cudaGetErrorString(cudaGetLastError());
         mems_destroy(h);
@@ -209,7 +210,7 @@ void mems_destroy(mems_handle_t h) {
     cudaFree(h->chains.x); cudaFree(h->chains.ll); cudaFree(h->chains.scale); cudaFree(h->chains.lambda);
     cudaFree(h->chains.win_acc); cudaFree(h->chains.adapt_i); cudaFree(h->chains.acc_count);
     cudaFree(h->chains.scale_cw); cudaFree(h->chains.lambda_cw); cudaFree(h->chains.win_cw);
-    cudaFree(h->chains.llc); cudaFree(h->chains.prom_count);
+    cudaFree(h->chains.llc); cudaFree(h->chains.prom_count); cudaFree(h->chains.rows_eval);
     cudaFree(h->dev_coarse);
     delete h->host_coarse;
     delete h;
@@ -382,6 +383,7 @@ int mems_init_chains(mems_handle_t h, const double* x0_dev, double scale0, uint6
     const int C = h->chains.C;
     CwInit cw;
     for (int p = 0; p < MEMS_PMAX; ++p) cw.s[p] = h->cw_scale[p];
+    CUDA_TRY(cudaMemsetAsync(h->chains.rows_eval, 0, sizeof(unsigned long long), st));
     init_chains_kernel<<<(C + 255) / 256, 256, 0, st>>>(h->chains, h->host_pb.c.P, x0_dev, scale0, cw);
     CUDA_TRY(cudaGetLastError());
     MemsLaunchCtx ctx = make_ctx(h, stream);
@@ -606,5 +608,17 @@ int mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep
 }
 
 int64_t mems_launch_count(mems_handle_t h) { return h ? h->launches : 0; }
+
+int mems_rows_evaluated(mems_handle_t h, uint64_t* rows, void* stream) {
+    if (!h || !rows) return fail(MEMS_E_INVALID, "null argument");
+    if (!h->have_chains) return fail(MEMS_E_STATE, "call mems_init_chains first");
+    DEVICE_SCOPE(h->cfg.device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, h->chains.rows_eval, sizeof(v), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *rows = (uint64_t)v;
+    return MEMS_OK;
+}
 
 }  // extern "C"

@@ -79,6 +79,7 @@ struct MemsChains {
     int* win_cw;          // [P][C]
     double* llc;          // [C] delayed acceptance: coarse log-likelihood of the current state
     unsigned int* prom_count;  // [C] delayed acceptance: proposals promoted to the fine stage
+    unsigned long long* rows_eval;  // [1] surrogate rows (chain, time point) evaluated by run launches since init_chains
     unsigned long long seed;
     unsigned long long chain_id0;
 };

@@ -128,8 +128,11 @@ fp32_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs 
                 if (batch_pass_is_coarse_model(ra, sub))       // DA first stage on the FFT surrogate: S_c for every chain
                     coarse_fft_pass(ra.coarse, P, T, &sm.cb.xp[0][0], MEMS_NCMAX, nullptr, ncv, sm.Spart, sm.act, tid, NT,
                                     [] { __syncthreads(); });
-                else
-                    eval_batch(sm, s_yobs, s_ts, P, T, batch_pass_stride(ra, sub), b7, nc, ncv, true, nullptr, c0);
+                else {
+                    const int stride = batch_pass_stride(ra, sub);      // (this path evaluates out-of-box proposals too)
+                    if (tid == 0) atomicAdd(ch.rows_eval, (unsigned long long)ncv * (unsigned long long)((T + stride - 1) / stride));
+                    eval_batch(sm, s_yobs, s_ts, P, T, stride, b7, nc, ncv, true, nullptr, c0);
+                }
                 if (tid < ncv) batch_post(sm.cb, sm.c, ch, ra, c0, tid, s, sub, sm.Spart[tid]);
                 __syncthreads();
             }

@@ -34,33 +34,36 @@
 
 namespace {
 
-// CTA organisation (round 2): two independent groups per CTA; each owns one batch of chains at a time and two TMEM tile
-// slots.  Three kinds of warps:
-//   server warps  (16 per CTA, shared by both groups)  the epilogue of every tanh layer of every tile of all four slots.
-//                 A server warp has a fixed ROLE (TMEM lane quarter = warp % 4 -- a hardware rule -- and column half
-//                 (warp / 4) % 2: a thread owns 32 of the 64 accumulator columns of its row) but no fixed slot: it
-//                 claims the next finished accumulator of ANY slot for its role (two warps per role compete through a
-//                 per-slot, per-role sequence counter).  Stateless, so a group that is busy with accept/reject or waits
-//                 for the tensor core never idles them -- measured in round 1/2: with warps tied to a group the XU
-//                 pipe (one exponential per activation) was busy 60 % of the time, against 78 % for the epilogue alone;
-//   control warps (4 per group)  the per-tile work (partial output-layer dots -> residual against y_obs -> squared sum,
-//                 layer-1 operand of the slot's next tile) and the per-chain Metropolis-Hastings bookkeeping between
-//                 passes (proposals, accept/reject, adaptation, thinned stores);
-//   MMA issuer    (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit for whichever of the
-//                 group's slots has its next A operand complete.
-// Hand-offs are mbarriers: control -> issuer (bar_At) -> tensor core -> servers (bar_D) -> issuer (bar_Ah) ... -> servers
-// -> control (bar_T).  Groups never synchronise with each other.
+// CTA organisation (round 2).  A CTA works on two batches of chains at a time ("groups": proposals, accept/reject,
+// adaptation are per group) that SHARE four TMEM tile slots (64 accumulator + 64 operand columns each) and the warps
+// that do the tile arithmetic:
+//   server teams  (2 teams x 8 warps)  the epilogue of every tanh layer of every tile in any slot.  A server warp has a
+//                 fixed role inside its team (TMEM lane quarter = warp % 4 -- a hardware rule -- and column half
+//                 (warp / 4) % 2: a thread owns 32 of the 64 accumulator columns of its row); the team's leader warp
+//                 claims the next finished accumulator of ANY slot and the team processes it together (a gang: an A
+//                 operand is complete only when all eight roles have delivered).  Servers hold no per-chain state, so
+//                 a group that is busy with accept/reject, or slots that wait for the tensor core, never idle them while
+//                 another slot has work -- with warps tied to one group's two slots (round 1) the XU pipe (one exponential
+//                 per activation) was busy 60 % of the time, against 78 % for the epilogue arithmetic alone;
+//   control warps (4 per group)  own the group's pass: acquire free slots from the shared pool, stage layer-1 operands,
+//                 turn the servers' partial output-layer dots into residuals and squared sums, release slots, and do the
+//                 per-chain Metropolis-Hastings bookkeeping between passes.  While one group is between passes the other
+//                 may hold all four slots;
+//   MMA issuer    (1 warp)  32 lanes converged, one elected lane issues tcgen05.mma / commit for whichever slot has its next
+//                 A operand complete.
+// Hand-offs are mbarriers per slot: control -> issuer (bar_At) -> tensor core -> servers (bar_D) -> issuer (bar_Ah) ... ->
+// servers -> control (bar_T).  Groups never synchronise with each other.
 constexpr int NGROUP = 2;
-constexpr int GSLOT = 2;                       // tile slots per group
-constexpr int NSLOT = NGROUP * GSLOT;
+constexpr int NSLOT = 4;                       // TMEM tile slots per CTA, shared by the groups
 constexpr int NH = 2;                          // column halves of the server warps
-constexpr int NROLE = 4 * NH;                  // server roles (lane quarter, column half)
-constexpr int SERVERS_PER_ROLE = 2;
-constexpr int STHREADS = 32 * NROLE * SERVERS_PER_ROLE;   // 512 server threads
+constexpr int NROLE = 4 * NH;                  // server roles (lane quarter, column half) = warps per team
+constexpr int NTEAM = 2;
+constexpr int STHREADS = 32 * NROLE * NTEAM;   // 512 server threads
 constexpr int GTHREADS = 128;                  // control threads per group = rows of a tile
 constexpr int NWORKER = STHREADS + NGROUP * GTHREADS;     // 768
-constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group = 832
+constexpr int NTHREADS = NWORKER + 32;         // + the MMA issuer warp = 800
 constexpr int ITEMS_PER_TILE = MEMS_HIDDEN;    // accumulators a slot delivers per tile (one per tanh layer)
+constexpr int PICK_RING = 8;                   // leader -> team mailbox depth (a leader is at most NSLOT items ahead)
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -75,18 +78,21 @@ constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
 // instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
+struct SlotSmem {
+    unsigned long long bar_At;         // control -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
+    unsigned long long bar_Ah;         // servers -> MMA issuer: A operand of the slot's next layer is in TMEM
+    unsigned long long bar_D;          // tensor core -> servers: an accumulator of the slot is complete (every layer)
+    unsigned long long bar_T;          // servers -> control: the partial output-layer dots of the slot's tile are in xchg
+    unsigned int next;                 // accumulators of the slot already claimed by a server team (a sequence number)
+    unsigned int tiles_done;           // tiles the slot has completed (parity of bar_T for its next user)
+    float xchg[NH][128];               // partial output-layer dots of the two column halves (servers -> control)
+    double R2[128];                    // dense passes: squared residual of every row of the slot's tile
+};
+
 struct GroupSmem {
     ChainBatch cb;
     double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (control threads)
-    double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
-    float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves (servers -> control)
-    unsigned long long bar_At[GSLOT];  // control -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
-    unsigned long long bar_Ah[GSLOT];  // servers -> MMA issuer: A operand of the slot's next layer is in TMEM
-    unsigned long long bar_D[GSLOT];   // tensor core -> servers: an accumulator of the slot is complete (every layer)
-    unsigned long long bar_T[GSLOT];   // servers -> control: the partial output-layer dots of the slot's tile are in xchg
-    unsigned long long bar_S;          // control -> MMA issuer: ctrl_tiles of the next pass is valid
-    unsigned int next[GSLOT][NROLE];   // per role: accumulators of the slot already claimed by a server (a sequence number)
-    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
+    int grab;                          // control thread 0 -> the group's control threads: slot just acquired (-1: none)
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
@@ -107,9 +113,12 @@ struct TcSmem {
     float pad_[3];
     MemsConsts c;
     GroupSmem grp[NGROUP];
+    SlotSmem slot[NSLOT];
     unsigned long long bar_w;
     uint32_t tmem_base;
-    unsigned int done;                 // bit g: group g has no more work (servers leave when all bits are set)
+    unsigned int done;                 // bit g: group g has no more work (servers and issuer leave when all bits are set)
+    unsigned int free_slots;           // bit s: slot s is in the pool
+    unsigned int pick[NTEAM][PICK_RING];   // leader -> team: (pick number + 1) << 8 | item, item = slot * 8 + layer, 0xFF = leave
     // followed by: double yobs[T]; float ts[T];
 };
 

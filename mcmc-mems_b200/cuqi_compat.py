@@ -217,61 +217,119 @@ class Samples:
 
 
 class BatchedSamples:
-    """C chains at once: ``.samples`` is ``(C, dim, Ns)``; indexing yields per-chain :class:`Samples`."""
+    """C chains at once: ``.samples`` is ``(C, dim, Ns)``; indexing yields per-chain :class:`Samples`.
 
-    def __init__(self, samples, loglike_eval, acc_rate, scale):
-        self.samples = np.asarray(samples, np.float64)
-        self.loglike_eval = loglike_eval
+    The draws stay where the sampler wrote them -- a device tensor ``[Ns, dim, C]`` (chain-minor, the kernel's coalesced
+    layout) -- until somebody asks for the numpy view: ``burnthin`` is a strided view, ``mean`` / ``std`` /
+    ``compute_ess`` / ``compute_rhat`` reduce on the device, and ``.samples`` is materialised once (one transposing copy
+    on the device, one pinned device-to-host copy).  Built from a host array it behaves exactly as before.
+    """
+
+    def __init__(self, samples, loglike_eval, acc_rate, scale, device_samples=None, device_loglike=None):
+        self._samples = None if samples is None else np.asarray(samples, np.float64)
+        self._loglike = loglike_eval
+        self._dev = device_samples              # torch [Ns, dim, C] f64 or None
+        self._dev_ll = device_loglike           # torch [Ns, C] f64 (already with the additive constants) or None
         self.acc_rate = np.asarray(acc_rate)
         self.scale = np.asarray(scale)
 
+    # -- lazy host views ---------------------------------------------------------------------
+    @staticmethod
+    def _to_host(t):
+        import torch
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=False)
+        return out.numpy()
+
+    @property
+    def samples(self):
+        if self._samples is None:
+            self._samples = self._to_host(self._dev.permute(2, 1, 0).contiguous())      # (C, dim, Ns)
+        return self._samples
+
+    @property
+    def loglike_eval(self):
+        if self._loglike is None and self._dev_ll is not None:
+            self._loglike = self._to_host(self._dev_ll.t().contiguous())                # (C, Ns)
+        return self._loglike
+
+    @property
+    def shape(self):
+        if self._dev is not None:
+            Ns, P, C = self._dev.shape
+            return (C, P, Ns)
+        return self._samples.shape
+
     def __len__(self):
-        return self.samples.shape[0]
+        return self.shape[0]
 
     def __getitem__(self, c) -> Samples:
-        ll = None if self.loglike_eval is None else self.loglike_eval[c]
-        return Samples(self.samples[c], ll, float(self.acc_rate[c]), float(self.scale[c]))
+        ll = self.loglike_eval
+        return Samples(self.samples[c], None if ll is None else ll[c], float(self.acc_rate[c]), float(self.scale[c]))
 
     def __iter__(self):
         return (self[c] for c in range(len(self)))
 
     def burnthin(self, Nb, Nt=1):
-        ll = None if self.loglike_eval is None else self.loglike_eval[:, Nb::Nt]
-        return BatchedSamples(self.samples[:, :, Nb::Nt], ll, self.acc_rate, self.scale)
+        if self._dev is not None:
+            ll = None if self._dev_ll is None else self._dev_ll[Nb::Nt]
+            return BatchedSamples(None, None, self.acc_rate, self.scale, self._dev[Nb::Nt], ll)
+        ll = None if self._loglike is None else self._loglike[:, Nb::Nt]
+        return BatchedSamples(self._samples[:, :, Nb::Nt], ll, self.acc_rate, self.scale)
 
     def mean(self):
-        return self.samples.mean(axis=(0, 2))
+        if self._dev is not None:
+            return self._dev.mean(dim=(0, 2)).cpu().numpy()
+        return self._samples.mean(axis=(0, 2))
 
     def std(self):
-        return self.samples.transpose(1, 0, 2).reshape(self.samples.shape[1], -1).std(axis=1)
+        if self._dev is not None:
+            m = self._dev.mean(dim=(0, 2), keepdim=True)
+            return ((self._dev - m) ** 2).mean(dim=(0, 2)).sqrt().cpu().numpy()
+        return self._samples.transpose(1, 0, 2).reshape(self._samples.shape[1], -1).std(axis=1)
 
-    def _device_samples(self, device):
+    def device_samples(self, device: int = 0):
+        """The draws as a device tensor ``[Ns, dim, C]`` (no copy when the sampler left them there)."""
         import torch
-        return torch.as_tensor(np.ascontiguousarray(self.samples.transpose(2, 1, 0))).to(f"cuda:{device}")   # [Ns, P, C]
+        if self._dev is not None:
+            return self._dev if self._dev.is_contiguous() else self._dev.contiguous()
+        return torch.as_tensor(np.ascontiguousarray(self._samples.transpose(2, 1, 0))).to(f"cuda:{device}")
+
+    _device_samples = device_samples
 
     def compute_ess(self, on_device: Optional[bool] = None, device: int = 0):
-        """Bulk effective sample size per parameter over all chains (arviz's default, rank-normalised).  Large batches
-        (or ``on_device=True``) are ranked and reduced on the GPU (``diagnostics_device.ess_bulk``): shipping 10^6
-        chains to arviz is the bottleneck the device path removes."""
-        C, P, Ns = self.samples.shape
+        """Bulk effective sample size per parameter over all chains (arviz's default, rank-normalised).  Large batches,
+        device-resident draws (or ``on_device=True``) are ranked and reduced on the GPU (``diagnostics_device.ess_bulk``):
+        shipping 10^6 chains to arviz is the bottleneck the device path removes."""
+        C, P, Ns = self.shape
         if on_device is None:
-            on_device = C * Ns > 2_000_000
+            on_device = self._dev is not None or C * Ns > 2_000_000
         if not on_device:
             return np.array([diagnostics.ess_bulk(self.samples[:, j, :]) for j in range(P)])
         from . import diagnostics_device
-        return diagnostics_device.ess_bulk(self._device_samples(device))
+        return diagnostics_device.ess_bulk(self.device_samples(device))
 
     def compute_rhat(self, on_device: Optional[bool] = None, device: int = 0):
-        C, P, Ns = self.samples.shape
+        C, P, Ns = self.shape
         if on_device is None:
-            on_device = C * Ns > 2_000_000
+            on_device = self._dev is not None or C * Ns > 2_000_000
         if not on_device:
             return np.array([diagnostics.rhat_rank(self.samples[:, j, :]) for j in range(P)])
         from . import diagnostics_device
-        return diagnostics_device.rhat_rank(self._device_samples(device))
+        return diagnostics_device.rhat_rank(self.device_samples(device))
 
 
 # -- sampler ---------------------------------------------------------------------------------
+_ENGINES: dict = {}        # (surrogate, chains, path, device, sampler setup) -> MHEngine, oldest first
+_ENGINE_CACHE = 4
+
+
+def close_engines():
+    """Release the cached GPU engines (handles, device buffers)."""
+    while _ENGINES:
+        _ENGINES.pop(next(iter(_ENGINES))).close()
+
+
 class MH:
     """``cuqi.sampler.MH`` look-alike running on the GPU.
 
@@ -304,11 +362,28 @@ class MH:
     _sampler = SAMPLER_MH
 
     def _engine(self, C) -> MHEngine:
+        """One engine (handle, device buffers, weight image) per (surrogate, chain count, path, device, sampler setup);
+        later calls with the same setup only refresh the problem constants."""
         cov = self.proposal._dense_cov(self.dim)
-        eng = MHEngine(self.spec, self.target.data, self.target.sigma2, self.target.prior.low,
-                       self.target.prior.high, cov, n_chains=C, path=self.path, device=self.device)
-        self._configure(eng)
+        key = (id(self.spec), int(C), int(self.path), int(self.device), self._sampler, self._engine_key())
+        eng = _ENGINES.get(key)
+        args = (self.target.data, self.target.sigma2, self.target.prior.low, self.target.prior.high, cov)
+        if eng is None:
+            while len(_ENGINES) >= _ENGINE_CACHE:
+                _ENGINES.pop(next(iter(_ENGINES))).close()
+            eng = MHEngine(self.spec, *args, n_chains=C, path=self.path, device=self.device)
+            self._configure(eng)
+            eng._problem_args = None
+            _ENGINES[key] = eng
+        sig = tuple(np.asarray(a, np.float64).tobytes() for a in args)
+        if getattr(eng, "_problem_args", None) != sig:
+            if eng._problem_args is not None:
+                eng.set_problem(*args)
+            eng._problem_args = sig
         return eng
+
+    def _engine_key(self):
+        return ()
 
     def _configure(self, eng: MHEngine):
         pass
@@ -316,60 +391,71 @@ class MH:
     def _adapt_window(self, N):
         return int(0.1 * N)
 
-    def sample(self, N, Nb=0):
+    def sample(self, N, Nb=0, Nt=1):
         if self.scale is None:
             raise ValueError("scale must be set for non-adaptive sampling")
-        return self._run(N, Nb, adapt=False)
+        return self._run(N, Nb, Nt, adapt=False)
 
-    def sample_adapt(self, N, Nb=0):
+    def sample_adapt(self, N, Nb=0, Nt=1):
+        """``N`` samples after ``Nb`` burn-in updates, like ``cuqi.sampler.MH.sample_adapt``.  Extension: ``Nt`` keeps
+        every ``Nt``-th of them (what ``Samples.burnthin(0, Nt)`` would select) without ever storing the others."""
         if self.scale is None:
             self.scale = 0.1
-        return self._run(N, Nb, adapt=True)
+        return self._run(N, Nb, Nt, adapt=True)
 
-    def _run(self, N, Nb, adapt):
-        x0 = np.atleast_2d(self.x0)
+    def _run(self, N, Nb, Nt, adapt):
+        import torch
+        x0 = np.atleast_2d(self.x0) if not isinstance(self.x0, torch.Tensor) else self.x0.reshape(-1, self.dim)
         if x0.shape[1] != self.dim:
             raise ValueError(f"x0 must have {self.dim} entries per chain")
+        if N < 1 or Nb < 0 or Nt < 1:
+            raise ValueError("need N >= 1, Nb >= 0, Nt >= 1")
         C = x0.shape[0]
+        single = (not isinstance(self.x0, torch.Tensor)) and np.asarray(self.x0).ndim == 1
         eng = self._engine(C)
-        try:
-            eng.init_chains(x0, scale0=float(self.scale), seed=self.seed, chain_id0=self.chain_id0)
-            Na = self._adapt_window(N) if adapt else 0
-            Ns = N + Nb
-            const = eng.loglik_const + eng.logprior_const
+        scale0 = np.asarray(self.scale, np.float64)
+        eng.init_chains(x0, scale0=float(scale0.reshape(-1)[0]), seed=self.seed, chain_id0=self.chain_id0)
+        Na = self._adapt_window(N) if adapt else 0
+        const = eng.loglik_const + eng.logprior_const
+        per = self.dim if self._sampler == SAMPLER_CWMH else 1                       # CWMH counts decisions per component
+        # cuqi: samples[:, 0] = x0, then N + Nb - 1 updates; the first Nb samples are dropped.  Kept sample k (k = 0, Nt,
+        # 2 Nt, ... < N) is the state after Nb + k updates.
+        n_keep = (N - 1) // Nt + 1
+        dev = f"cuda:{eng.device}"
+        smp = torch.empty(n_keep, self.dim, C, dtype=torch.float64, device=dev)
+        ll = torch.empty(n_keep, C, dtype=torch.float64, device=dev)
+        if Nb > 0:                                                                    # burn-in: only its last state is kept;
+            if Nb > 1:                                                                # cuqi's acc[Nb:] starts with update Nb's decision
+                eng.run_into(Nb - 1, Na, Nb, None, None)
+            acc0 = eng.accept_count()
+            eng.run_into(1, Na, 1, smp[:1], ll[:1])
+        else:
             st0 = eng.state()
-            pre = []
-            if Nb > 0:                                   # samples[:, :Nb] are dropped by CUQIpy
-                eng.run(Nb - 1, Na, 1, keep_samples=False) if Nb > 1 else None
-                a1 = eng.state()["accept_count"].cpu().numpy().astype(np.int64)
-                smp, ll = eng.run(Ns - Nb, Na, 1, keep_samples=True, keep_loglik=True)
-                acc_kept = eng.state()["accept_count"].cpu().numpy().astype(np.int64) - a1
-            else:
-                smp, ll = eng.run(Ns - 1, Na, 1, keep_samples=True, keep_loglik=True)
-                pre = [(st0["x"].cpu().numpy(), st0["loglik"].cpu().numpy())]
-                per = self.dim if self._sampler == SAMPLER_CWMH else 1                       # CWMH counts per component
-                acc_kept = eng.state()["accept_count"].cpu().numpy().astype(np.int64) + per   # acc[0] = 1
-            st = eng.state()
-            S = np.empty((C, self.dim, N))
-            LL = np.empty((C, N))
-            k = 0
-            for xs, l0 in pre:
-                S[:, :, 0] = xs.T
-                LL[:, 0] = l0
-                k = 1
-            if smp is not None:
-                S[:, :, k:] = smp.cpu().numpy().transpose(2, 1, 0)
-                LL[:, k:] = ll.cpu().numpy().T
-            LL = LL + const
-            acc_rate = acc_kept / float(N * (self.dim if self._sampler == SAMPLER_CWMH else 1))
+            smp[0].copy_(st0["x"])
+            ll[0].copy_(st0["loglik"])
+            acc0 = None
+        done = 0
+        if n_keep > 1:
+            eng.run_into((n_keep - 1) * Nt, Na, Nt, smp[1:], ll[1:])
+            done = (n_keep - 1) * Nt
+        if N - 1 - done > 0:                                                          # the tail cuqi still samples (and adapts on)
+            eng.run_into(N - 1 - done, Na, N, None, None)
+        st = eng.state()
+        acc_kept = st["accept_count"].to(torch.int64)
+        acc_kept = acc_kept - acc0.to(torch.int64) if acc0 is not None else acc_kept + per   # acc[0] = 1 of cuqi
+        acc_rate = (acc_kept.double() / float(N * per)).cpu().numpy()
+        if self._sampler == SAMPLER_CWMH:
+            scale = eng.aux_state()["scale_cw"].t().contiguous().cpu().numpy()                # [C, dim], cuqi keeps the vector
+            self.cw_scale = scale[0].copy()
+        else:
             scale = st["scale"].cpu().numpy()
-            self.scale = float(scale[0]) if C == 1 else scale
-        finally:
-            eng.close()
-        if np.asarray(self.x0).ndim == 1:
+        self.scale = (float(scale[0]) if scale.ndim == 1 else scale[0]) if C == 1 else scale
+        ll += const
+        if single:
             print("\nAverage acceptance rate:", acc_rate[0], "MCMC scale:", scale[0], "\n")
-            return Samples(S[0], LL[0], float(acc_rate[0]), float(scale[0]), self.target.model.domain_geometry)
-        return BatchedSamples(S, LL, acc_rate, scale)
+            return Samples(smp[:, :, 0].t().cpu().numpy(), ll[:, 0].cpu().numpy(), float(acc_rate[0]),
+                           scale[0] if scale.ndim > 1 else float(scale[0]), self.target.model.domain_geometry)
+        return BatchedSamples(None, None, acc_rate, scale, device_samples=smp, device_loglike=ll)
 
 
 class DelayedAcceptanceMH(MH):
@@ -387,6 +473,9 @@ class DelayedAcceptanceMH(MH):
         self.coarse_model, self.coarse_scaler = coarse_model, coarse_scaler
         if (coarse_model is None) != (coarse_scaler is None):
             raise ValueError("give both coarse_model and coarse_scaler or neither")
+
+    def _engine_key(self):
+        return ("da", self.stride, id(self.coarse_model))
 
     def _configure(self, eng):
         if self.coarse_model is not None:
@@ -409,6 +498,9 @@ class CWMH(MH):
             raise ValueError("CWMH on the GPU supports CUQIpy's default Normal(location, scale) proposal only")
         super().__init__(target, None, 1.0, x0, dim, **k)
         self.cw_scale = np.broadcast_to(np.asarray(scale, np.float64), (self.dim,)).copy()
+
+    def _engine_key(self):
+        return ("cw", tuple(float(v) for v in self.cw_scale))
 
     def _configure(self, eng):
         eng.set_sampler(SAMPLER_CWMH, cw_scale=self.cw_scale)

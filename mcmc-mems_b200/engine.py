@@ -289,6 +289,12 @@ class MHEngine:
                                           _stream(self.device)), "mems_get_state")
         return {"x": x, "loglik": ll, "scale": sc, "accept_count": ac, "steps_done": int(steps.value)}
 
+    def accept_count(self):
+        """Accepted updates per chain since ``init_chains`` (device tensor, int32)."""
+        ac = self._new(self.C, dtype=torch.int32)
+        _lib.check(self._L.mems_get_state(self._h, None, None, None, _ptr(ac), None, _stream(self.device)), "mems_get_state")
+        return ac
+
     def aux_state(self):
         """Variant-specific state: per-component scales (CWMH), coarse log-likelihood and promotions (DA)."""
         sc = self._new(self.P, self.C)
@@ -296,6 +302,12 @@ class MHEngine:
         pc = self._new(self.C, dtype=torch.int32)
         _lib.check(self._L.mems_get_aux(self._h, _ptr(sc), _ptr(llc), _ptr(pc), _stream(self.device)), "mems_get_aux")
         return {"scale_cw": sc, "loglik_coarse": llc, "promote_count": pc}
+
+    def rows_evaluated(self) -> int:
+        """Surrogate rows (chain, time point) evaluated by ``run`` launches since ``init_chains`` (synchronises)."""
+        v = C.c_uint64(0)
+        _lib.check(self._L.mems_rows_evaluated(self._h, C.byref(v), _stream(self.device)), "mems_rows_evaluated")
+        return int(v.value)
 
     @property
     def launches(self) -> int:

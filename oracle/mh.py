@@ -227,11 +227,13 @@ def cwmh_sample(logd, x0, N, Nb=0, scale=1.0, z=None, log_u=None, rng=None, adap
 # reference: PARITY UNPINNED)
 # --------------------------------------------------------------------------
 def da_sample(logd_fine, logd_coarse, x0, N, Nb=0, scale=1.0, xi=None, log_u=None, rng=None,
-              chol=None, return_trace=False):
+              chol=None, return_trace=False, adapt=False):
     """Two-stage MH.  Stage 1: promote iff ``log_u1 <= min(0, lc* - lc)``.
     Stage 2 (promoted only): accept iff ``log_u2 <= min(0, (lf* - lf) - (lc* - lc))``.
+    ``adapt``: the vanishing adaptation of ``MH._sample_adapt`` (window ``int(0.1*N)``, target 0.234) on the
+    final accept decisions -- the definition the device library uses for adaptive delayed acceptance.
 
-    log_u: ``[Ns-1, 2]``.  Returns samples, fine target, acceptance rate, promote rate.
+    log_u: ``[Ns-1, 2]``.  Returns samples, fine target, acceptance rate, promote rate (``adapt``: final scale appended).
     """
     x0 = np.asarray(x0, np.float64)
     dim = x0.size
@@ -253,6 +255,9 @@ def da_sample(logd_fine, logd_coarse, x0, N, Nb=0, scale=1.0, xi=None, log_u=Non
     tc[0] = logd_coarse(x0)
     acc[0] = 1
     prom[0] = 1
+    Na = int(0.1 * N) if adapt else 0
+    lambd = scale
+    i = idx = 0
     for s in range(Ns - 1):
         x_star = samples[:, s] + scale * xi[s]
         c_star = logd_coarse(x_star)
@@ -263,7 +268,15 @@ def da_sample(logd_fine, logd_coarse, x0, N, Nb=0, scale=1.0, xi=None, log_u=Non
             # second-stage ratio: [pi(x*) pi~(x)] / [pi(x) pi~(x*)]
             if decide(log_u[s, 1], (f_star - tf[s]) - (c_star - tc[s]), 0.0):
                 samples[:, s + 1], tf[s + 1], tc[s + 1], acc[s + 1] = x_star, f_star, c_star, 1
+        if Na > 0 and (s + 1) % Na == 0:
+            hat = np.mean(acc[idx:idx + Na])
+            lambd = math.exp(math.log(lambd) + (hat - 0.234) / math.sqrt(i + 1))
+            scale = min(lambd, 1.0)
+            i += 1
+            idx += Na
     out = (samples[:, Nb:], tf[Nb:], acc[Nb:].mean(), prom[Nb:].mean())
+    if adapt:
+        out = out + (scale,)
     if return_trace:
         return out + (acc, prom)
     return out

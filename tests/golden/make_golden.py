@@ -174,6 +174,11 @@ def main():
                                  "scale": [0.1314504627358983, 0.12692327229893097, 0.12892139843753464,
                                            0.12530442202049047, 0.1256356121192231],
                                  "rhat": [1.00452344, 1.00266526, 1.00371555]}
+    pins["qfactor_printed"] = {"acc": [0.3486666666666667, 0.3541666666666667, 0.35283333333333333, 0.35733333333333334,
+                                       0.3546666666666667],
+                               "scale": [0.20871315242186197, 0.2091576605505331, 0.21424495688396644, 0.22466504907059892,
+                                         0.21541593183414806],
+                               "rhat": [1.00353547, 1.00247405, 1.00237344, 1.00205655]}
     json.dump(pins, open(os.path.join(HERE, "pins.json"), "w"), indent=1)
 
 

@@ -132,8 +132,9 @@ def check_explicit_cwmh(pb, x0, cw_scale, z, log_u, smp, llp, dec, band):
     cur = np.asarray(x0, np.float64).copy()
     ll_cur = _ll_of(pb, cur)
     res = {"flips": 0, "near_ties": 0, "max_ll_err": 0.0, "state_err": 0.0}
+    cw_scale = np.asarray(cw_scale, np.float64)
     for s in range(S):
-        x_o = cur + np.asarray(cw_scale)[None, :] * z[s]
+        x_o = cur + (cw_scale[s] if cw_scale.ndim == 3 else cw_scale[None, :]) * z[s]     # [S,C,P]: per-step scales (adaptive runs)
         for p in range(P):
             prop = cur.copy()
             prop[:, p] = x_o[:, p]
@@ -177,8 +178,9 @@ def check_explicit_da(pb, x0, scale, stride, xi, log_u, smp, llp, dec, band, coa
         coarse_ll = lambda X: _ll_of(pb, X, stride)   # noqa: E731
     lf, lc = _ll_of(pb, cur), coarse_ll(cur)
     res = {"flips": 0, "near_ties": 0, "max_ll_err": 0.0, "state_err": 0.0, "promoted": 0, "accepted": 0}
+    scale = np.asarray(scale, np.float64)
     for s in range(S):
-        prop = cur + scale * xi[s]
+        prop = cur + (scale[s][:, None] if scale.ndim == 2 else scale) * xi[s]             # [S,C]: per-step scales (adaptive runs)
         lc_star, lf_star = coarse_ll(prop), _ll_of(pb, prop)
         fin = np.isfinite(lc_star)
         assert np.array_equal(np.isfinite(llp[s, 0]), fin)
@@ -205,3 +207,26 @@ def check_explicit_da(pb, x0, scale, stride, xi, log_u, smp, llp, dec, band, coa
                 lf[c], lc[c] = lf_star[c], lc_star[c]
         res["state_err"] = max(res["state_err"], float(np.max(np.abs(smp[s].T - cur))))
     return res
+
+
+def cuqi_scale_trajectory(dec, Na, scale0, target, first=1.0):
+    """Scale used by every update of an adaptive run, recomputed from its decisions with the CUQIpy 0.8.0 rule
+    (MH._sample_adapt / CWMH._sample_adapt): dec [S, ...] 0/1, acc[0] = `first` belongs to the first window; every Na
+    updates lambda <- exp(log lambda + (mean(acc[idx:idx+Na]) - target)/sqrt(i+1)), scale = min(lambda, 1).
+    Returns (scale_steps [S, ...], final scale [...])."""
+    dec = np.asarray(dec, np.float64)
+    S = dec.shape[0]
+    acc = np.concatenate([np.full((1,) + dec.shape[1:], first), dec])
+    lam = np.broadcast_to(np.asarray(scale0, np.float64), dec.shape[1:]).copy()
+    scale = lam.copy()
+    steps = np.empty_like(dec)
+    i = idx = 0
+    for s in range(S):
+        steps[s] = scale
+        if Na > 0 and (s + 1) % Na == 0:
+            hat = acc[idx:idx + Na].mean(axis=0)
+            lam = np.exp(np.log(lam) + (hat - target) / np.sqrt(i + 1))
+            scale = np.minimum(lam, 1.0)
+            i += 1
+            idx += Na
+    return steps, scale

@@ -1,0 +1,282 @@
+"""Round-2 parity tests (B200): adaptive component-wise MH and adaptive delayed acceptance replayed against the oracle,
+the drop-in ``MH.sample_adapt(N, Nb)`` against ``oracle.mh_sample_adapt`` on the device's own random stream, a
+component-wise invariance test that can fail in both directions, the Q-factor notebook's statistics, and the posterior
+agreement of the notebook workflow with Monte-Carlo error bounds.
+
+CUQIpy (cuqipy==0.8.0, reference README.md:36) is not vendored: its semantics are restated from memory in ``oracle/``
+ and pinned statistically by the numbers the reference notebooks printed (K3/K4); component-wise MH and
+delayed acceptance have no reference implementation at all -- their parity is against the oracle's
+definition only.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import helpers  # noqa: E402
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+PATHS = [0, 1]
+PATH_IDS = ["fp32", "tc"]
+BAND = {0: 2e-3, 1: 0.02}       # near-tie band |log u - min(0, dl)| inside which a decision may legitimately differ
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _inputs(pb, C, S, seed, jitter=0.05):
+    rng = np.random.default_rng(seed)
+    L = np.linalg.cholesky(pb["cov"])
+    P = len(pb["low"])
+    x0 = pb["x_opts"][np.arange(C) % len(pb["x_opts"])] + jitter * rng.standard_normal((C, P)) @ L.T
+    return rng, L, x0
+
+
+# ----------------------------------------------------------------------------- (i) adaptive CWMH / DA
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_adaptive_componentwise_mh_replay(path):
+    """CWMH with per-component adaptation (cuqi CWMH._sample_adapt semantics: window Na, target 0.21/d + 0.23, acc[:, 0] = 1
+    in the first window).  (a) every decision against the oracle's rule with the scales recomputed from the kernel's own
+    decisions, final per-component scales to 1e-13; (b) whole trajectories against oracle.cwmh_sample(adapt=True) for the
+    chains without a near-tie."""
+    from mcmc_mems_b200 import engine as E
+    from oracle import cwmh_sample
+    pb = helpers.load_problem("geometric")
+    C, N, P = 12, 501, 3                           # oracle: Na = int(0.012 * N) = 6
+    S, Na = N - 1, int(0.012 * N)
+    rng, _, x0 = _inputs(pb, C, S, 21)
+    cw = 0.5 * np.sqrt(pb["sigma2"] * np.diag(pb["cov"]))
+    z = rng.standard_normal((S, C, P))
+    log_u = np.log(rng.random((S, C, P)))
+    eng = helpers.engine(pb, C, path)
+    eng.set_sampler(E.SAMPLER_CWMH, cw_scale=cw)
+    eng.init_chains(x0, scale0=0.1)
+    smp, llp, dec = eng.run_explicit(z.transpose(0, 2, 1), log_u.transpose(0, 2, 1), adapt_window=Na)
+    smp, llp, dec = smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy()
+    target = 0.21 / P + 0.23
+    steps, final = helpers.cuqi_scale_trajectory(dec.transpose(0, 2, 1), Na, np.broadcast_to(cw, (C, P)), target)   # [S,C,P]
+    got = eng.aux_state()["scale_cw"].cpu().numpy().T                                                                # [C,P]
+    assert np.allclose(got, final, rtol=1e-13, atol=0)
+    assert np.ptp(got / cw, axis=0).max() > 0.05                 # chains adapted differently
+    res = helpers.check_explicit_cwmh(pb, x0, steps, z, log_u, smp, llp, dec, BAND[path])
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    # (b) the oracle sampler end to end on the same randomness
+    logd = helpers.oracle_logd(pb)
+    same = 0
+    for c in range(C):
+        s_o, _, acc_o, sc_o, acc_tr, _ = cwmh_sample(logd, x0[c], N, 0, scale=cw, z=z[:, c], log_u=log_u[:, c], adapt=True, return_trace=True)
+        if np.array_equal(acc_tr[:, 1:].T, dec[:, :, c]):
+            same += 1
+            assert np.array_equal(s_o[:, 1:].T, smp[:, :, c])    # states bit-exact
+            assert np.allclose(sc_o, got[c], rtol=1e-13, atol=0)
+    assert same >= C // 2, same                                  # the rest met a near-tie (checked per decision above)
+    eng.close()
+
+
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("coarse", ["strided", "fft"])
+def test_adaptive_delayed_acceptance_replay(path, coarse):
+    """Delayed acceptance with scale adaptation (window Na, target 0.234, on the final decisions): every stage-1 and
+    stage-2 decision against the oracle with the scales recomputed from the kernel's own decisions; final scales equal the
+    CUQIpy formula to 1e-13; whole trajectories against oracle.da_sample(adapt=True) for chains without a near-tie."""
+    from mcmc_mems_b200 import engine as E
+    from oracle import da_sample
+    name = "geometric" if coarse == "strided" else "qfactor"
+    pb = helpers.load_problem(name)
+    C, N, stride = 10, 241, 5
+    S, Na = N - 1, int(0.1 * N)
+    rng, L, x0 = _inputs(pb, C, S, 33)
+    P = x0.shape[1]
+    xi = rng.standard_normal((S, C, P)) @ L.T
+    log_u = np.log(rng.random((S, C, 2)))
+    eng = helpers.engine(pb, C, path)
+    coarse_ll = None
+    if coarse == "fft":
+        cf = helpers.fft_coarse()
+        eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+        eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+        coarse_ll = helpers.coarse_ll_fn(pb, cf)
+    else:
+        eng.set_sampler(E.SAMPLER_DA, da_stride=stride)
+    eng.init_chains(x0, scale0=0.2)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u.transpose(0, 2, 1), adapt_window=Na)
+    smp, llp, dec = smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy()
+    steps, final = helpers.cuqi_scale_trajectory(dec[:, 1, :], Na, np.full(C, 0.2), 0.234)
+    got = eng.state()["scale"].cpu().numpy()
+    assert np.allclose(got, final, rtol=1e-13, atol=0) and len(np.unique(np.round(got, 10))) > 2
+    res = helpers.check_explicit_da(pb, x0, steps, stride, xi, log_u, smp, llp, dec, BAND[path], coarse_ll=coarse_ll)
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert 0 < res["accepted"] <= res["promoted"]
+    fine = lambda x: float(helpers._ll_of(pb, np.asarray(x)[None])[0])               # noqa: E731
+    crs = (lambda x: float(coarse_ll(np.asarray(x)[None])[0])) if coarse_ll else (lambda x: float(helpers._ll_of(pb, np.asarray(x)[None], stride)[0]))
+    same = 0
+    for c in range(C):
+        o = da_sample(fine, crs, x0[c], N, 0, 0.2, xi=xi[:, c], log_u=log_u[:, c], adapt=True, return_trace=True)
+        acc_tr, prom_tr = o[5], o[6]
+        if np.array_equal(acc_tr[1:], dec[:, 1, c]) and np.array_equal(prom_tr[1:], dec[:, 0, c]):
+            same += 1
+            assert np.array_equal(o[0][:, 1:].T, smp[:, :, c]) and o[4] == pytest.approx(got[c], rel=1e-13)
+    assert same >= C // 2, same
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- (ii) the drop-in, decision for decision
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("Nb", [0, 37])
+def test_dropin_sample_adapt_equals_oracle_on_the_device_stream(path, Nb):
+    """``MH(target, proposal, x0).sample_adapt(N, Nb)`` (identification.ipynb:300-302) for ONE chain, against
+    ``oracle.mh_sample_adapt`` fed with the random stream the device consumed (``mems_draw``): samples, log-densities,
+    acceptance rate and adapted scale -- including the burn-in split (samples[:, Nb:], acc[Nb:]) of CUQIpy."""
+    from mcmc_mems_b200 import MH, Gaussian, cuqi_compat, fixtures
+    from oracle import mh_sample_adapt
+    pb = helpers.load_problem("geometric")
+    fx = fixtures.load_fixture("geometric")
+    post = fixtures.posterior_of(fx)
+    N = 400
+    x0 = pb["x_opts"][1]
+    logd = helpers.oracle_logd(pb)
+    matched = False
+    for seed in (11, 12, 13, 14):          # a near-tie inside the band lets trajectories diverge legitimately: next seed
+        mh = MH(target=post, proposal=Gaussian(np.zeros(3), pb["cov"]), x0=x0, seed=seed, path=path)
+        s = mh.sample_adapt(N, Nb)
+        eng = mh._engine(1)                                    # the cached engine of that call
+        xi, lu = eng.draw(0, N + Nb - 1)
+        xi, lu = xi.cpu().numpy()[:, :, 0], lu.cpu().numpy()[:, 0]
+        so, te, acc, sc, acc_tr, prop = mh_sample_adapt(logd, x0, N, Nb, xi=xi, log_u=lu, return_trace=True)
+        assert s.samples.shape == (3, N)
+        moved = np.any(np.diff(s.samples, axis=1) != 0, axis=0)     # decisions: moved <=> accepted
+        want = acc_tr[Nb + 1:] == 1
+        if not np.array_equal(moved, want):
+            j = int(np.argmax(moved != want))                       # first differing decision = update Nb + j
+            margin = abs(lu[Nb + j] - min(0.0, prop[Nb + j] - te[j]))
+            assert margin <= BAND[path], (seed, j, margin)
+            continue
+        assert np.array_equal(s.samples, so)                    # bit-exact states (x + scale*xi in two roundings, like numpy)
+        assert np.allclose(s.loglike_eval, te, rtol=0, atol=0.05)
+        assert s.acc_rate == pytest.approx(acc, abs=1e-12) and s.scale == pytest.approx(sc, rel=1e-12)
+        matched = True
+        break
+    assert matched, "every seed met a near-tie"
+    cuqi_compat.close_engines()
+
+
+def test_dropin_thinning_extension_selects_the_same_draws():
+    """``sample_adapt(N, Nb, Nt)`` keeps exactly ``sample_adapt(N, Nb).burnthin(0, Nt)`` (same seed), batched."""
+    from mcmc_mems_b200 import MH, Gaussian, cuqi_compat, fixtures
+    fx = fixtures.load_fixture("geometric")
+    post = fixtures.posterior_of(fx)
+    x0 = np.tile(fx.x_opts, (4, 1))
+    prop = Gaussian(np.zeros(3), fx.cov)
+    full = MH(post, prop, x0=x0, seed=5).sample_adapt(301, 20)
+    thin = MH(post, prop, x0=x0, seed=5).sample_adapt(301, 20, Nt=7)
+    assert full.shape == (20, 3, 301) and thin.shape == (20, 3, 43)
+    assert np.array_equal(full.burnthin(0, 7).samples, thin.samples)
+    assert np.array_equal(full.loglike_eval[:, ::7], thin.loglike_eval)
+    assert np.array_equal(full.acc_rate, thin.acc_rate) and np.array_equal(full.scale, thin.scale)
+    assert np.allclose(thin.mean(), thin.samples.mean(axis=(0, 2)), rtol=1e-12)
+    cuqi_compat.close_engines()
+
+
+# ----------------------------------------------------------------------------- (iii) CWMH invariance, both directions
+def test_componentwise_mh_samples_the_same_posterior_two_sided():
+    """Component-wise moves crawl along the strongly correlated posterior ridge (correlation 0.99), so a short run is
+    under-dispersed; 40 000 updates per chain are enough to compare location AND spread with random-walk MH in both
+    directions (a sampler that collapsed, or one that over-dispersed, fails)."""
+    from mcmc_mems_b200 import engine as E
+    pb = helpers.load_problem("geometric")
+    C = 1024
+    sd = np.sqrt(pb["sigma2"] * np.diag(pb["cov"]))
+    x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
+    out = {}
+    for name, sampler, kw, scale0, burn, N, thin in (("mh", E.SAMPLER_MH, {}, 0.128, 2000, 6000, 20),
+                                                     ("cw", E.SAMPLER_CWMH, {"cw_scale": 1.5 * sd}, 0.1, 10000, 30000, 100)):
+        eng = helpers.engine(pb, C, 1)
+        eng.set_sampler(sampler, **kw)
+        eng.init_chains(x0, scale0=scale0, seed=123)
+        eng.run(burn, 0, burn, keep_samples=False)
+        smp, _ = eng.run(N, 0, thin)
+        S = smp.cpu().numpy().transpose(1, 0, 2).reshape(3, -1)
+        out[name] = (S.mean(axis=1), S.std(axis=1))
+        eng.close()
+    assert np.all(np.abs(out["cw"][0] - out["mh"][0]) < 0.15 * out["mh"][1]), out
+    assert np.all(np.abs(out["cw"][1] / out["mh"][1] - 1.0) < 0.10), out
+
+
+# ----------------------------------------------------------------------------- (iv) Q-factor notebook statistics
+@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+def test_qfactor_adaptive_mh_statistics_match_notebook(path):
+    """The 4-parameter notebook (tests/Xaccelerometer_quality_factor/identification.ipynb:478-506): acceptance
+    0.349-0.357, scale 0.209-0.225, samples/sample_10.npy.  Same bands as the CPU oracle test (the notebook's proposal
+    covariance and observation are not reproducible, see tests/test_oracle_cpu.py::test_k3_k4_qfactor_statistics), plus
+    agreement with the oracle sampler on the same observation within Monte-Carlo error."""
+    from oracle import mh_sample_adapt
+    pb = helpers.load_problem("qfactor")
+    C, N = 256, 6000
+    x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
+    eng = helpers.engine(pb, C, path)
+    eng.init_chains(x0, scale0=0.1, seed=4242)
+    smp, _ = eng.run(N - 1, adapt_window=600)
+    st = eng.state()
+    acc = (st["accept_count"].cpu().numpy() + 1) / N
+    scale = st["scale"].cpu().numpy()
+    pr = helpers.pins()["qfactor_printed"]
+    assert abs(acc.mean() - np.mean(pr["acc"])) <= 0.04, acc.mean()
+    assert abs(np.median(scale) / np.mean(pr["scale"]) - 1.0) <= 0.25, np.median(scale)
+    S = smp.cpu().numpy()[1000::5]
+    pooled = S.transpose(1, 0, 2).reshape(4, -1)
+    ratio = pooled.std(axis=1) / np.array(helpers.pins()["qfactor_sample_10"]["std"])
+    assert np.all(np.abs(ratio[[0, 1, 3]] - 1.0) < 0.25) and abs(ratio[2] - 1.0) < 0.6, ratio
+    L = np.linalg.cholesky(pb["cov"])
+    o = [mh_sample_adapt(helpers.oracle_logd(pb), pb["x_opts"][k], N, 0, rng=np.random.default_rng(k), chol=L) for k in range(3)]
+    ref = np.hstack([r[0][:, 1000::5] for r in o])
+    se = ref.std(axis=1) / np.sqrt(120)                   # ~ESS of 3 thinned oracle chains
+    assert np.all(np.abs(pooled.mean(axis=1) - ref.mean(axis=1)) < 5 * se)
+    assert np.all(np.abs(pooled.std(axis=1) / ref.std(axis=1) - 1.0) < 0.15)
+    assert abs(acc.mean() - np.mean([r[2] for r in o])) < 0.015 and abs(np.median(scale) / np.mean([r[3] for r in o]) - 1.0) < 0.06
+    eng.close()
+
+
+# ----------------------------------------------------------------------------- (v) posterior agreement, notebook workflow
+def test_notebook_workflow_posterior_agrees_with_oracle_within_mc_error():
+    """identification.ipynb cells 12-14 end to end through the drop-in: 6000 adaptive updates from the five LSQ optima,
+    burn 1000, thin 5 -- oracle (CUQIpy semantics, numpy, 5 chains) vs the GPU drop-in with 5 and with 2000 chains.
+    Means within Monte-Carlo error of the 5-chain oracle run, spreads within 10 %, acceptance and scale within the
+    notebook's printed ranges widened by the chain-to-chain scatter."""
+    from mcmc_mems_b200 import MH, Gaussian, cuqi_compat, fixtures
+    from mcmc_mems_b200 import diagnostics
+    from oracle import mh_sample_adapt
+    pb = helpers.load_problem("geometric")
+    fx = fixtures.load_fixture("geometric")
+    post = fixtures.posterior_of(fx)
+    prop = Gaussian(np.zeros(3), fx.cov)
+    N, Nb, Nt = 6000, 1000, 5
+    L = np.linalg.cholesky(pb["cov"])
+    o = [mh_sample_adapt(helpers.oracle_logd(pb), pb["x_opts"][k], N, 0, rng=np.random.default_rng(100 + k), chol=L) for k in range(5)]
+    ref = np.stack([r[0][:, Nb::Nt] for r in o])                                   # (5, 3, 1000)
+    ess = np.array([diagnostics.ess_bulk(ref[:, j, :]) for j in range(3)])
+    ref_mean, ref_std = ref.transpose(1, 0, 2).reshape(3, -1).mean(axis=1), ref.transpose(1, 0, 2).reshape(3, -1).std(axis=1)
+    se = ref_std / np.sqrt(ess)
+    five = MH(post, prop, x0=fx.x_opts, seed=9).sample_adapt(N, 0).burnthin(Nb, Nt)
+    many = MH(post, prop, x0=np.tile(fx.x_opts, (400, 1)), seed=10).sample_adapt(N, 0).burnthin(Nb, Nt)
+    assert five.shape == (5, 3, 1000) and many.shape == (2000, 3, 1000)
+    rh = five.compute_rhat(on_device=False)
+    assert np.all(rh < 1.03), rh                                                    # notebook: 1.0027-1.0045
+    assert np.all(five.compute_ess(on_device=False) > 300)                          # notebook: 183-464 per chain, x5 chains
+    for b, k in ((five, 4.5), (many, 4.0)):
+        assert np.all(np.abs(b.mean() - ref_mean) < k * se * (np.sqrt(2) if b is five else 1.0)), (b.mean(), ref_mean, se)
+    assert np.all(np.abs(many.std() / ref_std - 1.0) < 0.10)
+    assert np.all(np.abs(many.std() / np.array(helpers.pins()["geometric_sample_10"]["std"]) - 1.0) < 0.15)
+    pr = helpers.pins()["geometric_printed"]
+    assert abs(many.acc_rate.mean() - np.mean(pr["acc"])) <= 0.02 and abs(np.median(many.scale) / np.mean(pr["scale"]) - 1.0) <= 0.10
+    assert abs(many.acc_rate.mean() - np.mean([r[2] for r in o])) < 0.01
+    cuqi_compat.close_engines()

@@ -78,12 +78,47 @@ def test_k3_k4_adaptive_mh_statistics():
     L = np.linalg.cholesky(pb["cov"])
     s, te, acc, sc = mh_sample_adapt(logd, pb["x_opts"][0], 6000, 0, rng=np.random.default_rng(0), chol=L)
     assert s.shape == (3, 6000) and te.shape == (6000,)
-    assert 0.24 <= acc <= 0.30          # notebook: 0.269-0.280
-    assert 0.110 <= sc <= 0.145         # notebook: 0.1253-0.1315
+    pr = helpers.pins()["geometric_printed"]                 # notebook: 0.269-0.280 / 0.1253-0.1315
+    assert abs(acc - np.mean(pr["acc"])) <= 0.02             # +-0.02 on the acceptance rate,
+    assert abs(sc / np.mean(pr["scale"]) - 1.0) <= 0.10      #               +-10 % on the adapted scale
     g = helpers.pins()["geometric_sample_10"]
     assert np.all(np.abs(s.std(axis=1) / np.array(g["std"]) - 1.0) < 0.25)
     # the first window contains acc[0] = 1 and the scale only changes every Na = 600 updates
     assert np.isfinite(te).all()
+
+
+def test_k3_k4_qfactor_statistics():
+    """K3/K4 of the 4-parameter Q-factor notebook (tests/Xaccelerometer_quality_factor/identification.ipynb:478-506:
+    acceptance 0.349-0.357, scale 0.209-0.225; samples/sample_10.npy).  CUQIpy semantics are restated from memory
+     and pinned only statistically; here the pin is looser than for the geometric problem because the
+    notebook's proposal is 10 x inv(J^T J) of a float32 3-point Jacobian (noise-dominated, utils.py:87-88) around an
+    UNSEEDED observation, neither of which the fixture can reproduce: +-0.04 on the acceptance rate, +-25 % on the
+    scale, spreads within 25 % (thickness, prior-truncated and noise-realisation dependent: 60 %)."""
+    pb = helpers.load_problem("qfactor")
+    logd = helpers.oracle_logd(pb)
+    L = np.linalg.cholesky(pb["cov"])
+    s, te, acc, sc = mh_sample_adapt(logd, pb["x_opts"][0], 6000, 0, rng=np.random.default_rng(0), chol=L)
+    pr = helpers.pins()["qfactor_printed"]
+    assert abs(acc - np.mean(pr["acc"])) <= 0.04, acc
+    assert abs(sc / np.mean(pr["scale"]) - 1.0) <= 0.25, sc
+    q = helpers.pins()["qfactor_sample_10"]                   # saved after burnthin(1000, 5)
+    ratio = s[:, 1000::5].std(axis=1) / np.array(q["std"])
+    assert np.all(np.abs(ratio[[0, 1, 3]] - 1.0) < 0.25) and abs(ratio[2] - 1.0) < 0.6, ratio
+    assert np.isfinite(te).all()
+
+
+def test_adaptive_delayed_acceptance_oracle_reduces_to_mh_rule():
+    """oracle.da_sample(adapt=True): with a coarse model equal to the fine one every promoted proposal is accepted, so
+    the chain and its adapted scale equal mh_sample_adapt's on the same randomness (the second uniform is unused)."""
+    mu, sd = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    logd = lambda x: float(-0.5 * np.sum(((x - mu) / sd) ** 2))
+    rng = np.random.default_rng(3)
+    N = 2000
+    xi = rng.standard_normal((N - 1, 2)) * sd
+    lu = np.log(rng.random((N - 1, 2)))
+    a = mh_sample_adapt(logd, mu, N, 0, 0.5, xi=xi, log_u=lu[:, 0])
+    b = da_sample(logd, logd, mu, N, 0, 0.5, xi=xi, log_u=np.stack([lu[:, 0], np.full(N - 1, -1e-300)], axis=1), adapt=True)
+    assert np.array_equal(a[0], b[0]) and a[3] == b[4] and a[2] == b[2]
 
 
 def test_explicit_randomness_is_reproducible():
