@@ -13,9 +13,9 @@
 //             against [b_hi; b_mid; b_lo]; 2*log2(e) is folded into weights and biases on the host so the
 //             accumulator is directly the exp2 argument of tanh(z) = 1 - 2/(2^(2z*log2 e) + 1).
 //   layer 1   the (P+1)->64 layer is a K=32 MMA over three-way-split scaled inputs.
-//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns), shared by the two batches of chains a CTA works on;
-//             two teams of eight stateless server warps run the epilogue of whichever slot has an accumulator ready,
-//             four control warps per batch own the passes, one warp issues the MMAs (mems_tc_device.cuh).
+//   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns) in two independent groups; per group eight
+//             hidden-layer warps, four tail warps (last tanh layer + output layer + residual + next tile's layer-1
+//             operand) and one MMA-issuer warp (mems_tc_device.cuh), handing a slot round by mbarriers.
 //   tail      64->1 output layer, residual against y_obs, squared-sum reduction in FP64, accept/reject
 //             and chain-state update (mems_common.cuh) all happen in the same kernel.
 //
@@ -52,158 +52,49 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-#ifndef MEMS_POLL_SLEEP
-#define MEMS_POLL_SLEEP 0          // nanoseconds an idle polling warp sleeps between scans (0 = spin)
-#endif
-__device__ __forceinline__ void poll_pause() {
-#if MEMS_POLL_SLEEP > 0
-    __nanosleep(MEMS_POLL_SLEEP);
-#endif
-}
-__device__ __forceinline__ unsigned int ld_volatile(const unsigned int* p) { return *reinterpret_cast<const volatile unsigned int*>(p); }
-constexpr unsigned int ALL_DONE = (1u << NGROUP) - 1u;
-
-// MMA issuer warp (all 32 lanes run the loop convergently; one elected lane issues): serves the four slots in whatever
-// order their A operands complete.  Layer 0 of a tile waits for a control warp's layer-1 operand (bar_At), layers 1..5 for
-// the server warps' A operands (bar_Ah); every accumulator is committed to the slot's bar_D.  Leaves when both groups are
-// done (nothing can be pending then).
-__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm) {
+// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues): for every
+// surrogate pass the group announces (ctrl_tiles via bar_S) it serves the group's two slots in the fixed order
+// the epilogue warps produce them; ctrl_tiles < 0 ends the loop.  `g` must be warp-uniform.
+// Per tile: layer 0 waits for the tail warps' layer-1 operand, layers 1..5 for the hidden warps' A operands; every
+// accumulator goes to the hidden warps (bar_Dh).
+__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
     const uint32_t wimg = smem_u32(sm.wimg);
-    const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
-    uint32_t ph = 0;                  // bits 0..3: bar_Ah parity per slot; bits 4..7: bar_At parity per slot
-    int layer[NSLOT];
-#pragma unroll
-    for (int s = 0; s < NSLOT; ++s) layer[s] = 0;
+    const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
+    uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S
     for (;;) {
-        bool any = false;
+        mbar_wait(&gs.bar_S, (ph >> 4) & 1u);
+        ph ^= 16u;
+        const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
+        if (n_tiles < 0) break;
+        const int n_pairs = (n_tiles + 1) >> 1;
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-            void* bar = (layer[s] == 0) ? (void*)&sm.slot[s].bar_At : (void*)&sm.slot[s].bar_Ah;
-            const uint32_t bit = (layer[s] == 0) ? (16u << s) : (1u << s);
-            uint32_t ok = 0;
-            if ((threadIdx.x & 31) == 0) ok = mbar_test(bar, (ph & bit) ? 1u : 0u) ? 1u : 0u;
-            ok = __shfl_sync(0xffffffffu, ok, 0);
-            if (ok) {
-                mbar_wait(bar, (ph & bit) ? 1u : 0u);              // every lane observes the completed phase (returns at once)
-                ph ^= bit;
-                tc_fence_after();
-                if (elect_one()) {
-                    issue_layer(wimg, base + s * 128, layer[s]);
-                    umma_commit(&sm.slot[s].bar_D);
-                }
-                __syncwarp();
-                layer[s] = (layer[s] + 1 == MEMS_HIDDEN) ? 0 : layer[s] + 1;
-                any = true;
-            }
-        }
-        if (!any) {
-            uint32_t d = 0;
-            if ((threadIdx.x & 31) == 0) d = ld_volatile(&sm.done);
-            if (__shfl_sync(0xffffffffu, d, 0) == ALL_DONE) break;
-            poll_pause();                   // (a protocol bug traps in the control warps' mbarrier watchdog)
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Server warps: the epilogue of any slot
-// ------------------------------------------------------------------------------------------
-// One item = one finished accumulator (slot, layer).  Hidden layers: accumulator -> tanh -> fp16 hi/lo split -> the
-// slot's next A operand (TMEM), then tell the issuer.  Last tanh layer: fused with the 64 -> 1 output layer; the
-// partial dot of the thread's 32 columns goes to shared memory for the control warps that own the tile.
-__device__ __forceinline__ void server_item(TcSmem& sm, int sl, int layer, int q, int h, int row) {
-    constexpr int NCOL = 64 / NH;                     // accumulator columns per thread
-    // the thread's columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain than the whole row keeps XU, FMA
-    // and ALU work of one warp interleaved: profiles/r02_microbench_*)
-    constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
-    SlotSmem& ss = sm.slot[sl];
-    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl * 128);
-    if (layer < MEMS_HIDDEN - 1) {
-#pragma unroll
-        for (int pc = 0; pc < NCOL / EC; ++pc) {
-            uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
-            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-            tc_wait_ld();
-            epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
-            tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
-            tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&ss.bar_Ah);
-    } else {
-        uint64_t acc = pk(0.0f, 0.0f);
-#pragma unroll
-        for (int pc = 0; pc < NCOL / EC; ++pc) {
-            uint32_t w[EC];
-            tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-            tc_wait_ld();
-#pragma unroll
-            for (int g8 = 0; g8 < EC / 8; ++g8)
-                acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
-        }
-        float oa, ob;
-        upk(acc, oa, ob);
-        ss.xchg[h][row] = oa + ob;
-        tc_fence_before();                                 // the accumulator has been read: the slot may be restaged
-        mbar_arrive(&ss.bar_T);                            // release: the store above is visible to the control warps
-    }
-}
-
-// item word of the team mailbox: slot | layer << 2 | accumulator-barrier parity << 5; 0xFF = leave
-__device__ __forceinline__ void server_loop(TcSmem& sm) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int team = warp / NROLE, role = warp % NROLE;
-    const int q = warp & 3, h = (warp >> 2) & 1;
-    const int row = q * 32 + lane;
-    unsigned int c = 0;                                    // picks consumed so far
-    int rot = team * (NSLOT / NTEAM);                      // the two leaders start their scans on different slots
-    for (;;) {
-        unsigned int item = 0;
-        if (role == 0) {                                   // team leader: claim the next finished accumulator of any slot
-            int found;
-            for (;;) {
-                found = -1;
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < NSLOT; ++k) {
-                        if (found < 0) {
-                            const int sl = (rot + k) & (NSLOT - 1);
-                            const unsigned int sq = ld_volatile(&sm.slot[sl].next);
-                            if (mbar_test(&sm.slot[sl].bar_D, sq & 1u) && atomicCAS(&sm.slot[sl].next, sq, sq + 1u) == sq)
-                                found = (int)((unsigned int)sl | ((sq % (unsigned int)ITEMS_PER_TILE) << 2) | ((sq & 1u) << 5));
+                for (int s = 0; s < GSLOT; ++s) {
+                    if (pair * 2 + s < n_tiles) {
+                        if (layer == 0) {
+                            mbar_wait(&gs.bar_At[s], (ph >> (2 + s)) & 1u);
+                            ph ^= (4u << s);
+                        } else {
+                            mbar_wait(&gs.bar_Ah[s], (ph >> s) & 1u);
+                            ph ^= (1u << s);
                         }
+                        tc_fence_after();
+                        if (elect_one()) {
+                            issue_layer(wimg, base + s * 128, layer);
+                            umma_commit(&gs.bar_Dh[s]);
+                        }
+                        __syncwarp();
                     }
-                    if (found < 0 && ld_volatile(&sm.done) == ALL_DONE) found = 0xFF;
                 }
-                found = __shfl_sync(0xffffffffu, found, 0);
-                if (found >= 0) break;
-                poll_pause();                              // idling is legitimate (e.g. passes on the coarse model only)
             }
-            item = (unsigned int)found;
-            if (lane == 0) *reinterpret_cast<volatile unsigned int*>(&sm.pick[team][c % PICK_RING]) = ((c + 1u) << 8) | item;
-            rot = (int)(item & 3u) + 1;                    // look at the other slots first next time
-        } else {                                           // follower: take the leader's picks in order
-            unsigned int v = 0;
-            for (;;) {
-                if (lane == 0) v = ld_volatile(&sm.pick[team][c % PICK_RING]);
-                v = __shfl_sync(0xffffffffu, v, 0);
-                if ((v >> 8) == c + 1u) break;
-                poll_pause();
-            }
-            item = v & 0xFFu;
         }
-        ++c;
-        if (item == 0xFFu) break;
-        const int sl = (int)(item & 3u), layer = (int)((item >> 2) & 7u);
-        mbar_wait(&sm.slot[sl].bar_D, (item >> 5) & 1u);   // every lane observes the completed phase (returns at once)
-        tc_fence_after();
-        server_item(sm, sl, layer, q, h, row);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// Control warps: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
+// Epilogue side: evaluate S[j] = sum_t (y_obs[t] - f(x_j)[t])^2 for the nc proposals in cb.xs
 // ------------------------------------------------------------------------------------------
 // K-slot of (term, input) in the layer-1 operand: terms 0..2 multiply W_hi, 3..4 multiply W_lo
 template <int P>
@@ -230,160 +121,177 @@ __device__ __forceinline__ void put_input(uint32_t (&a1)[16], int i, float v) {
 
 __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GTHREADS); }
 
-// Take a free slot out of the CTA's pool (all control threads of the group call; thread 0 decides).  Returns
-// slot | parity of the slot's bar_T << 8, or -1 when the pool is empty.
-__device__ __forceinline__ int group_acquire_slot(TcSmem& sm, GroupSmem& gs, int g, int row) {
-    if (row == 0) {
-        int got = -1;
-        unsigned int m = ld_volatile(&sm.free_slots);
-        while (m != 0u) {
-            const int b = __ffs((int)m) - 1;
-            const unsigned int old = atomicAnd(&sm.free_slots, ~(1u << b));
-            if (old & (1u << b)) { got = b; break; }
-            m = old & ~(1u << b);
-        }
-        if (got >= 0) {
-            __threadfence_block();                                     // acquire: the previous owner's tiles_done
-            got |= (int)((ld_volatile(&sm.slot[got].tiles_done) & 1u) << 8);
-        }
-        gs.grab = got;
-    }
-    group_bar_sync(g);
-    const int r = gs.grab;
-    group_bar_sync(g);
-    return r;
-}
-
-// The 128 control threads of group g drive one surrogate pass over the group's batch: thread `row` owns row `row` of every
-// tile = (chain slot row mod nce, time sub-row row / nce).  Tiles go through whatever slots the pool offers (up to all
-// four while the other group is between passes); results are consumed in tile order, so sums are deterministic.
+// The epilogue threads of group g evaluate one batch: gt < HTHREADS are the hidden-layer threads (row = gt % 128, column
+// half gt / 128), the rest the tail threads (row = gt - HTHREADS).  Row `row` of every tile is (chain slot row mod nce,
+// time sub-row row / nce).
 // compact: only the gs.nlive chains listed in gs.map take part (nce = gs.nlive): proposals outside the prior box and,
 // in the delayed-acceptance second stage, proposals the first stage did not promote cost nothing -- the tiles are
 // rebuilt from the live chains, so the pass shrinks with the promotion rate.  Result: gs.Sfin[chain].
 // DENSE (compact passes only): (time, chain) pairs are laid out back to back, row i of tile k is pair f = 128k + i
-// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A thread
-// then meets a different chain in every tile: the squared residuals of a tile go through shared memory (R2 of the slot)
-// and thread c < n_live adds the entries of chain slot c in time order (deterministic).
+// = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A tail
+// thread then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2)
+// and tail thread c < n_live adds the entries of chain slot c in time order (deterministic).
 template <int P, bool DENSE>
-__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int row, const double* s_yobs,
+__device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int gt, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
-                                              bool compact, float* y_out, int c0) {
+                                              bool compact, float* y_out, int c0, uint32_t& ph) {
+    const bool is_tail = gt >= HTHREADS;
+    const int row = is_tail ? gt - HTHREADS : (gt & 127);
     const int q = row >> 5;
     const int nce = compact ? gs.nlive : nc;          // chains laid out in the tiles (any value in 1..128)
     const int tpt = 128 / nce;                        // time points per tile
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
     const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
-    const uint32_t tL = sm.tmem_base + ((uint32_t)(q * 32) << 16);
-    const int jc = row % nce;                         // rows >= nce*tpt of a tile idle
-    const int sub = row / nce;
-    const int j = compact ? (int)gs.map[jc] : jc;     // batch-local chain index
-    const bool chain_live = (sub < tpt) && (compact || jc < ncv);
-    uint32_t a1[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a1[i] = 0u;
-    if (!DENSE) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
+    const int n_pairs = (n_tiles + 1) >> 1;
+    const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
+    if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
+        *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
+        mbar_arrive(&gs.bar_S);
     }
-    set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);           // ones that pick up b_hi, b_mid, b_lo
-    set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
-    set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
-    // layer-1 operand of `tile` into slot sl
-    auto stage_tile = [&](int sl, int tile) {
-        if (DENSE) {
-            const int f = tile * 128 + row;
-            const int ti = f / nce;
-            const bool ok = ti < Tn;
-            const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
-#pragma unroll
-            for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
-            put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
-        } else {
-            const int ti = tile * tpt + sub;
-            put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
-        }
-        tmem_st16(tL + (uint32_t)(sl * 128) + 64, a1);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&sm.slot[sl].bar_At);
-    };
 
-    // in-flight tiles [lo, hi): slot and bar_T parity of tile k in bits 3(k%4)..3(k%4)+2 of `fl`
-    uint32_t fl = 0;
-    auto fl_set = [&](int k, int sl, uint32_t par) { const int sh = 3 * (k & 3); fl = (fl & ~(7u << sh)) | (((uint32_t)sl | (par << 2)) << sh); };
-    int lo = 0, hi = 0;
-    double Sp = 0.0;
-    while (lo < n_tiles) {
-        // tile lo must be in flight; beyond that take what the pool offers, one attempt per consumed tile
-        bool tried = false;
-        while (hi < n_tiles && hi - lo < NSLOT && (hi == lo || !tried)) {
-            const int got = group_acquire_slot(sm, gs, g, row);
-            tried = true;
-            if (got >= 0) {
-                fl_set(hi, got & 0xFF, (uint32_t)(got >> 8) & 1u);
-                stage_tile(got & 0xFF, hi);
-                ++hi;
-                tried = false;                         // the pool had something: look again
-            } else if (hi == lo) {
-                poll_pause();
+    if (!is_tail) {
+        // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
+        constexpr int NCOL = 64 / NH;                 // accumulator columns per thread
+        const int h = gt >> 7;                        // column half
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+#pragma unroll
+                for (int s = 0; s < GSLOT; ++s) {
+                    if (pair * 2 + s < n_tiles) {
+                        const uint32_t tD = tD0 + s * 128;
+                        mbar_wait(&gs.bar_Dh[s], (ph >> s) & 1u);
+                        ph ^= (1u << s);
+                        tc_fence_after();
+                        // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain
+                        // than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
+                        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
+                        if (layer < MEMS_HIDDEN - 1) {
+#pragma unroll
+                            for (int pc = 0; pc < NCOL / EC; ++pc) {
+                                uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
+                                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                                tc_wait_ld();
+                                epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
+                                tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
+                                tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
+                            }
+                            tc_wait_st();
+                            tc_fence_before();
+                            mbar_arrive(&gs.bar_Ah[s]);
+                        } else {                               // last tanh layer . output weights: partial dot to the tail warps
+                            uint64_t acc = pk(0.0f, 0.0f);
+#pragma unroll
+                            for (int pc = 0; pc < NCOL / EC; ++pc) {
+                                uint32_t w[EC];
+                                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                                tc_wait_ld();
+#pragma unroll
+                                for (int g8 = 0; g8 < EC / 8; ++g8)
+                                    acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
+                            }
+                            float oa, ob;
+                            upk(acc, oa, ob);
+                            gs.xchg[s][h][row] = oa + ob;
+                            tc_fence_before();                 // the accumulator has been read: the slot may be restaged
+                            mbar_arrive(&gs.bar_X[s]);         // release: the store above is visible to the tail warps
+                        }
+                    }
+                }
             }
         }
-        const int sl = (int)((fl >> (3 * (lo & 3))) & 3u);
-        const uint32_t par = (fl >> (3 * (lo & 3) + 2)) & 1u;
-        SlotSmem& ss = sm.slot[sl];
-        mbar_wait(&ss.bar_T, par);
-        tc_fence_after();
-        const float o = ss.xchg[0][row] + ss.xchg[1][row] + sm.b7;
-        const int tile = lo;
-        if (DENSE) {
-            const int f = tile * 128 + row;
-            const int ti = f / nce;
-            double r2 = 0.0;
-            if (ti < Tn) {
-                const double r = s_yobs[ti * stride] - (double)o;
-                r2 = r * r;
-            }
-            ss.R2[row] = r2;
-            group_bar_sync(g);                                     // the tile's 128 residuals are in shared memory
-            if (row < nce) {                                       // chain slot `row`: its rows of this tile, in time order
-                int r0 = row - (tile * 128) % nce;
-                if (r0 < 0) r0 += nce;
-                for (int rr = r0; rr < 128; rr += nce) Sp += ss.R2[rr];
-            }
-            group_bar_sync(g);                                     // R2 of the slot may be rewritten by the slot's next user
-        } else {
-            const int ti = tile * tpt + sub;
-            const int t = ti * stride;
-            if (chain_live && ti < Tn) {
-                if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
-                const double r = s_yobs[t] - (double)o;
-                Sp = fma(r, r, Sp);
-            }
-        }
-        // the slot is free again: the group's next tile goes into it, or it returns to the pool
-        if (hi < n_tiles) {
-            fl_set(hi, sl, par ^ 1u);
-            stage_tile(sl, hi);
-            ++hi;
-        } else {
-            if (!DENSE) group_bar_sync(g);                         // every control thread has read the slot's partial dots
-            if (row == 0) {
-                ss.tiles_done = par ^ 1u;
-                __threadfence_block();                             // release: the next owner reads tiles_done
-                atomicOr(&sm.free_slots, 1u << sl);
-            }
-        }
-        ++lo;
-    }
-    if (DENSE) {
-        if (row < nce) gs.Sfin[gs.map[row]] = Sp;     // thread `row` summed chain slot `row` over all tiles
     } else {
-        gs.Spart[row] = Sp;
+        // ---- tail warps: layer-1 operands, last tanh layer + output layer, residuals
+        const int jc = row % nce;                     // rows >= nce*tpt of a tile idle
+        const int sub = row / nce;
+        const int j = compact ? (int)gs.map[jc] : jc; // batch-local chain index
+        const bool chain_live = (sub < tpt) && (compact || jc < ncv);
+        uint32_t a1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a1[i] = 0u;
+        if (!DENSE) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) put_input<P>(a1, p, (compact || jc < ncv) ? gs.cb.xs[p][j] : 0.0f);
+        }
+        set_half<P>(a1, 5 * (P + 1) + 0, 1.0f);       // ones that pick up b_hi, b_mid, b_lo
+        set_half<P>(a1, 5 * (P + 1) + 1, 1.0f);
+        set_half<P>(a1, 5 * (P + 1) + 2, 1.0f);
+        // layer-1 operand of `tile` into slot s
+        auto stage_tile = [&](int s, int tile) {
+            if (DENSE) {
+                const int f = tile * 128 + row;
+                const int ti = f / nce;
+                const bool ok = ti < Tn;
+                const int jj = ok ? (int)gs.map[f - ti * nce] : 0;
+#pragma unroll
+                for (int p = 0; p < P; ++p) put_input<P>(a1, p, ok ? gs.cb.xs[p][jj] : 0.0f);
+                put_input<P>(a1, P, s_ts[ok ? ti * stride : 0]);
+            } else {
+                const int ti = tile * tpt + sub;
+                put_input<P>(a1, P, s_ts[(ti < Tn && sub < tpt) ? ti * stride : 0]);
+            }
+            tmem_st16(tD0 + s * 128 + 64, a1);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&gs.bar_At[s]);
+        };
+#pragma unroll
+        for (int s = 0; s < GSLOT; ++s)
+            if (s < n_tiles) stage_tile(s, s);
+
+        double Sp = 0.0;
+        for (int pair = 0; pair < n_pairs; ++pair) {
+#pragma unroll 1
+            for (int s = 0; s < GSLOT; ++s) {
+                const int tile = pair * 2 + s;
+                if (tile < n_tiles) {
+                    mbar_wait(&gs.bar_X[s], (ph >> s) & 1u);
+                    ph ^= (1u << s);
+                    tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
+                    const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + sm.b7;
+                    if (DENSE) {
+                        const int f = tile * 128 + row;
+                        const int ti = f / nce;
+                        double r2 = 0.0;
+                        if (ti < Tn) {
+                            const double r = s_yobs[ti * stride] - (double)o;
+                            r2 = r * r;
+                        }
+                        gs.R2[s][row] = r2;
+                        named_bar_sync(3 + g, TTHREADS);               // the tile's 128 residuals are in shared memory
+                        if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
+                            int r0 = row - (tile * 128) % nce;
+                            if (r0 < 0) r0 += nce;
+                            for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
+                        }
+                        // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
+                    } else {
+                        const int ti = tile * tpt + sub;
+                        const int t = ti * stride;
+                        if (chain_live && ti < Tn) {
+                            if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                            const double r = s_yobs[t] - (double)o;
+                            Sp = fma(r, r, Sp);
+                        }
+                    }
+                    // this slot's D and A are free again: stage the layer-1 operand of its next tile
+                    const int nt = tile + GSLOT;
+                    if (nt < n_tiles) stage_tile(s, nt);
+                }
+            }
+        }
+        if (DENSE) {
+            if (row < nce) gs.Sfin[gs.map[row]] = Sp; // tail thread `row` summed chain slot `row` over all tiles
+        } else {
+            gs.Spart[row] = Sp;
+        }
+    }
+    if (!DENSE) {
         group_bar_sync(g);
-        if (row < nce) {
+        if (gt < nce) {
             double S = 0.0;                            // fixed order: time sub-rows ascending
-            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + row];
-            gs.Sfin[compact ? (int)gs.map[row] : row] = S;
+            for (int u = 0; u < tpt; ++u) S += gs.Spart[u * nce + gt];
+            gs.Sfin[compact ? (int)gs.map[gt] : gt] = S;
         }
     }
     group_bar_sync(g);                                 // Sfin[chain] may have been written by another thread
@@ -407,16 +315,16 @@ __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt,
     group_bar_sync(g);
 }
 
-// thread -> role:  tid < STHREADS: server warp (kind 0);  tid < NWORKER: control thread `row` of group g (kind 1);
-// else the MMA issuer warp (kind 2).  warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both
-// worker kinds.
-__device__ __forceinline__ int my_role(int& g, int& row) {
+// thread -> (group, index within the group's epilogue threads); issuer warps get gt = -1
+//   tid <  NGROUP*HTHREADS                : hidden threads, group = tid / HTHREADS, gt = tid % HTHREADS
+//   tid <  NWORKER                        : tail threads,   group = (tid - 512) / TTHREADS, gt = HTHREADS + row
+//   else                                  : MMA issuer warp of group (tid - NWORKER) / 32
+// (warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both worker kinds)
+__device__ __forceinline__ void my_role(int& g, int& gt) {
     const int tid = threadIdx.x;
-    if (tid < STHREADS) { g = 0; row = 0; return 0; }
-    if (tid < NWORKER) { g = (tid - STHREADS) / GTHREADS; row = (tid - STHREADS) % GTHREADS; return 1; }
-    g = 0;
-    row = 0;
-    return 2;
+    if (tid < NGROUP * HTHREADS) { g = tid / HTHREADS; gt = tid % HTHREADS; }
+    else if (tid < NWORKER) { g = (tid - NGROUP * HTHREADS) / TTHREADS; gt = HTHREADS + (tid - NGROUP * HTHREADS) % TTHREADS; }
+    else { g = (tid - NWORKER) >> 5; gt = -1; }
 }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
@@ -424,19 +332,17 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     if (tid == 0) {
-        for (int sl = 0; sl < NSLOT; ++sl) {
-            mbar_init(&sm.slot[sl].bar_At, GTHREADS);
-            mbar_init(&sm.slot[sl].bar_Ah, 32 * NROLE);
-            mbar_init(&sm.slot[sl].bar_T, 32 * NROLE);
-            mbar_init(&sm.slot[sl].bar_D, 1);
-            sm.slot[sl].next = 0u;
-            sm.slot[sl].tiles_done = 0u;
+        for (int g = 0; g < NGROUP; ++g) {
+            for (int s = 0; s < GSLOT; ++s) {
+                mbar_init(&sm.grp[g].bar_At[s], TTHREADS);
+                mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS);
+                mbar_init(&sm.grp[g].bar_Dh[s], 1);
+                mbar_init(&sm.grp[g].bar_X[s], HTHREADS);
+            }
+            mbar_init(&sm.grp[g].bar_S, 1);
+            sm.grp[g].ctrl_tiles = 0;
         }
-        for (int t = 0; t < NTEAM; ++t)
-            for (int k = 0; k < PICK_RING; ++k) sm.pick[t][k] = 0u;
-        sm.free_slots = (1u << NSLOT) - 1u;
         mbar_init(&sm.bar_w, 1);
-        sm.done = 0u;
         sm.c = pb.c;
         fence_barrier_init();
     }
@@ -481,15 +387,15 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     const int T = sm.c.T, nc = ra.nc;
     const int nbatch = (ch.C + nc - 1) / nc;
     int g, gt;
-    const int kind = my_role(g, gt);
+    my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (kind == 0) {
-        server_loop(sm);
-    } else if (kind == 2) {
-        mma_issuer_loop(sm);
+    if (gt < 0) {
+        const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
+        uint32_t ph = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, ch.C - c0);
@@ -511,9 +417,9 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                         const int Tn = (T + stride - 1) / stride, tpt = 128 / gs.nlive;
                         if (gt == 0) atomicAdd(ch.rows_eval, (unsigned long long)gs.nlive * (unsigned long long)Tn);
                         if ((gs.nlive * Tn + 127) / 128 < (Tn + tpt - 1) / tpt)
-                            tc_eval_group<P, true>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0);
+                            tc_eval_group<P, true>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
                         else
-                            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0);
+                            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
                     }
                     if (gt < ncv) batch_post(gs.cb, sm.c, ch, ra, c0, gt, s, sub, (any && gs.cb.live[gt] == 1) ? gs.Sfin[gt] : 0.0);
                 }
@@ -521,7 +427,10 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
             batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
         }
         group_bar_sync(g);
-        if (gt == 0) atomicOr(&sm.done, 1u << g);
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
+        }
     }
     tc_epilogue_free(sm);
 }
@@ -540,15 +449,15 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
     const int T = sm.c.T;
     const int nbatch = (n + nc - 1) / nc;
     int g, gt;
-    const int kind = my_role(g, gt);
+    my_role(g, gt);
     GroupSmem& gs = sm.grp[g];
     const int gid = blockIdx.x * NGROUP + g, gstride = gridDim.x * NGROUP;
 
-    if (kind == 0) {
-        server_loop(sm);
-    } else if (kind == 2) {
-        mma_issuer_loop(sm);
+    if (gt < 0) {
+        const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
+        mma_issuer_loop(sm, sm.grp[gw], gw);
     } else {
+        uint32_t ph = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
             const int c0 = batch * nc;
             const int ncv = min(nc, n - c0);
@@ -564,7 +473,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
                 gs.cb.live[gt] = 1;
             }
             group_bar_sync(g);
-            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0);
+            tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, false, y_out, c0, ph);
             if (gt < ncv && ll_out) {
                 // a strided (coarse) pass is rescaled to the full trace length, as in the DA first stage
                 const int Tn = (T + stride - 1) / stride;
@@ -573,7 +482,10 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
             }
         }
         group_bar_sync(g);
-        if (gt == 0) atomicOr(&sm.done, 1u << g);
+        if (gt == 0) {
+            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
+            mbar_arrive(&gs.bar_S);
+        }
     }
     tc_epilogue_free(sm);
 }

@@ -34,36 +34,28 @@
 
 namespace {
 
-// CTA organisation (round 2).  A CTA works on two batches of chains at a time ("groups": proposals, accept/reject,
-// adaptation are per group) that SHARE four TMEM tile slots (64 accumulator + 64 operand columns each) and the warps
-// that do the tile arithmetic:
-//   server teams  (2 teams x 8 warps)  the epilogue of every tanh layer of every tile in any slot.  A server warp has a
-//                 fixed role inside its team (TMEM lane quarter = warp % 4 -- a hardware rule -- and column half
-//                 (warp / 4) % 2: a thread owns 32 of the 64 accumulator columns of its row); the team's leader warp
-//                 claims the next finished accumulator of ANY slot and the team processes it together (a gang: an A
-//                 operand is complete only when all eight roles have delivered).  Servers hold no per-chain state, so
-//                 a group that is busy with accept/reject, or slots that wait for the tensor core, never idle them while
-//                 another slot has work -- with warps tied to one group's two slots (round 1) the XU pipe (one exponential
-//                 per activation) was busy 60 % of the time, against 78 % for the epilogue arithmetic alone;
-//   control warps (4 per group)  own the group's pass: acquire free slots from the shared pool, stage layer-1 operands,
-//                 turn the servers' partial output-layer dots into residuals and squared sums, release slots, and do the
-//                 per-chain Metropolis-Hastings bookkeeping between passes.  While one group is between passes the other
-//                 may hold all four slots;
-//   MMA issuer    (1 warp)  32 lanes converged, one elected lane issues tcgen05.mma / commit for whichever slot has its next
-//                 A operand complete.
-// Hand-offs are mbarriers per slot: control -> issuer (bar_At) -> tensor core -> servers (bar_D) -> issuer (bar_Ah) ... ->
-// servers -> control (bar_T).  Groups never synchronise with each other.
+// CTA organisation (round 2): two independent groups per CTA; each owns one batch of chains at a time, two TMEM tile
+// slots (ping-pong: the epilogue of one slot overlaps the MMAs of the other) and three kinds of warps:
+//   hidden warps (8 per group)  epilogue of the six tanh layers: TMEM lane quarter = warp % 4 (a hardware rule), column half
+//                               = (warp / 4) % 2 -- a thread owns 32 of the 64 accumulator columns of its row.  The last layer
+//                               is fused with the 64 -> 1 output layer and leaves two partial dots per row in shared memory;
+//   tail warps   (4 per group)  what happens once per tile and needs no exponentials: residual against y_obs, its squared
+//                               sum, and the layer-1 operand of the slot's next tile -- plus, between passes, the per-chain
+//                               bookkeeping.  In round 1 the hidden warps did this too, serially (10 % of their time,
+//                               profiles/r02_*), and the XU pipe idled meanwhile.  (Giving the tail warps the last tanh
+//                               layer as well was measured: its latency stalls the slot, 38.9 M vs this layout);
+//   MMA issuer   (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit.
+// Hand-offs are mbarriers (tail -> issuer -> hidden -> issuer ... -> tail); groups never synchronise with each other, so
+// one group's accept/reject section overlaps the other group's tensor work.  The first min(n_chains, 128) hidden
+// threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
 constexpr int NGROUP = 2;
-constexpr int NSLOT = 4;                       // TMEM tile slots per CTA, shared by the groups
-constexpr int NH = 2;                          // column halves of the server warps
-constexpr int NROLE = 4 * NH;                  // server roles (lane quarter, column half) = warps per team
-constexpr int NTEAM = 2;
-constexpr int STHREADS = 32 * NROLE * NTEAM;   // 512 server threads
-constexpr int GTHREADS = 128;                  // control threads per group = rows of a tile
-constexpr int NWORKER = STHREADS + NGROUP * GTHREADS;     // 768
-constexpr int NTHREADS = NWORKER + 32;         // + the MMA issuer warp = 800
-constexpr int ITEMS_PER_TILE = MEMS_HIDDEN;    // accumulators a slot delivers per tile (one per tanh layer)
-constexpr int PICK_RING = 8;                   // leader -> team mailbox depth (a leader is at most NSLOT items ahead)
+constexpr int GSLOT = 2;                       // tile slots per group
+constexpr int NH = 2;                          // column halves of the hidden warps
+constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
+constexpr int TTHREADS = 128;                  // tail threads per group
+constexpr int GTHREADS = HTHREADS + TTHREADS;  // 384: the threads of a group that meet at group barriers
+constexpr int NWORKER = NGROUP * GTHREADS;     // 768
+constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group = 832
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -78,21 +70,17 @@ constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
 // instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-struct SlotSmem {
-    unsigned long long bar_At;         // control -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
-    unsigned long long bar_Ah;         // servers -> MMA issuer: A operand of the slot's next layer is in TMEM
-    unsigned long long bar_D;          // tensor core -> servers: an accumulator of the slot is complete (every layer)
-    unsigned long long bar_T;          // servers -> control: the partial output-layer dots of the slot's tile are in xchg
-    unsigned int next;                 // accumulators of the slot already claimed by a server team (a sequence number)
-    unsigned int tiles_done;           // tiles the slot has completed (parity of bar_T for its next user)
-    float xchg[NH][128];               // partial output-layer dots of the two column halves (servers -> control)
-    double R2[128];                    // dense passes: squared residual of every row of the slot's tile
-};
-
 struct GroupSmem {
     ChainBatch cb;
-    double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (control threads)
-    int grab;                          // control thread 0 -> the group's control threads: slot just acquired (-1: none)
+    double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (tail threads)
+    double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
+    unsigned long long bar_At[GSLOT];  // tail -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
+    unsigned long long bar_Ah[GSLOT];  // hidden -> MMA issuer: A operand of the slot's next layer is in TMEM
+    unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of the slot is complete
+    unsigned long long bar_X[GSLOT];   // hidden -> tail warps: partial output-layer dots of the slot's tile are in xchg
+    float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves
+    unsigned long long bar_S;          // group -> MMA issuer: ctrl_tiles of the next pass is valid
+    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
@@ -113,12 +101,9 @@ struct TcSmem {
     float pad_[3];
     MemsConsts c;
     GroupSmem grp[NGROUP];
-    SlotSmem slot[NSLOT];
     unsigned long long bar_w;
     uint32_t tmem_base;
-    unsigned int done;                 // bit g: group g has no more work (servers and issuer leave when all bits are set)
-    unsigned int free_slots;           // bit s: slot s is in the pool
-    unsigned int pick[NTEAM][PICK_RING];   // leader -> team: (pick number + 1) << 8 | item, item = slot * 8 + layer, 0xFF = leave
+    uint32_t pad2_;
     // followed by: double yobs[T]; float ts[T];
 };
 
@@ -149,16 +134,6 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");   // hardware-suspended wait, wakes on completion
 #endif
-    return ok != 0;
-}
-// Non-blocking: has the phase with this parity completed?
-__device__ __forceinline__ bool mbar_test(void* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
 // Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
