@@ -69,7 +69,7 @@ def test_adaptive_componentwise_mh_replay(path):
     assert np.allclose(got, final, rtol=1e-13, atol=0)
     assert np.ptp(got / cw, axis=0).max() > 0.05                 # chains adapted differently
     res = helpers.check_explicit_cwmh(pb, x0, steps, z, log_u, smp, llp, dec, BAND[path])
-    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert res["flips"] == 0 and res["state_err"] < 1e-13 and res["max_ll_err"] < 1e-3, res
     # (b) the oracle sampler end to end on the same randomness
     logd = helpers.oracle_logd(pb)
     same = 0
@@ -77,7 +77,7 @@ def test_adaptive_componentwise_mh_replay(path):
         s_o, _, acc_o, sc_o, acc_tr, _ = cwmh_sample(logd, x0[c], N, 0, scale=cw, z=z[:, c], log_u=log_u[:, c], adapt=True, return_trace=True)
         if np.array_equal(acc_tr[:, 1:].T, dec[:, :, c]):
             same += 1
-            assert np.array_equal(s_o[:, 1:].T, smp[:, :, c])    # states bit-exact
+            assert np.allclose(s_o[:, 1:].T, smp[:, :, c], rtol=1e-14, atol=0)
             assert np.allclose(sc_o, got[c], rtol=1e-13, atol=0)
     assert same >= C // 2, same                                  # the rest met a near-tie (checked per decision above)
     eng.close()
@@ -115,7 +115,9 @@ def test_adaptive_delayed_acceptance_replay(path, coarse):
     got = eng.state()["scale"].cpu().numpy()
     assert np.allclose(got, final, rtol=1e-13, atol=0) and len(np.unique(np.round(got, 10))) > 2
     res = helpers.check_explicit_da(pb, x0, steps, stride, xi, log_u, smp, llp, dec, BAND[path], coarse_ll=coarse_ll)
-    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    # (the scales come from numpy's exp / log here and from the device's in the kernel: equal to 1e-13, not to the bit,
+    # so a state may differ from the replay's in its last place)
+    assert res["flips"] == 0 and res["state_err"] < 1e-13 and res["max_ll_err"] < 1e-3, res
     assert 0 < res["accepted"] <= res["promoted"]
     fine = lambda x: float(helpers._ll_of(pb, np.asarray(x)[None])[0])               # noqa: E731
     crs = (lambda x: float(coarse_ll(np.asarray(x)[None])[0])) if coarse_ll else (lambda x: float(helpers._ll_of(pb, np.asarray(x)[None], stride)[0]))
@@ -125,7 +127,7 @@ def test_adaptive_delayed_acceptance_replay(path, coarse):
         acc_tr, prom_tr = o[5], o[6]
         if np.array_equal(acc_tr[1:], dec[:, 1, c]) and np.array_equal(prom_tr[1:], dec[:, 0, c]):
             same += 1
-            assert np.array_equal(o[0][:, 1:].T, smp[:, :, c]) and o[4] == pytest.approx(got[c], rel=1e-13)
+            assert np.allclose(o[0][:, 1:].T, smp[:, :, c], rtol=1e-14, atol=0) and o[4] == pytest.approx(got[c], rel=1e-13)
     assert same >= C // 2, same
     eng.close()
 
@@ -189,27 +191,41 @@ def test_dropin_thinning_extension_selects_the_same_draws():
 
 # ----------------------------------------------------------------------------- (iii) CWMH invariance, both directions
 def test_componentwise_mh_samples_the_same_posterior_two_sided():
-    """Component-wise moves crawl along the strongly correlated posterior ridge (correlation 0.99), so a short run is
-    under-dispersed; 40 000 updates per chain are enough to compare location AND spread with random-walk MH in both
-    directions (a sampler that collapsed, or one that over-dispersed, fails)."""
+    """Invariance of component-wise MH, in both directions.  The posterior is a ridge (smallest eigenvalue of its
+    correlation matrix 2e-4: a component's conditional std is 2-3 % of its marginal std), so single-component moves need
+    thousands of sweeps per independent draw and chains started at a point stay under-dispersed for a long time.  The test
+    therefore starts 1024 chains IN the posterior (final states of a random-walk MH run), lets adaptive CWMH run 40 000
+    sweeps -- long enough that the chains forget where they started (checked) -- and requires location and spread to still
+    equal the random-walk sampler's: a sampler that collapsed or over-dispersed fails."""
     from mcmc_mems_b200 import engine as E
     pb = helpers.load_problem("geometric")
     C = 1024
     sd = np.sqrt(pb["sigma2"] * np.diag(pb["cov"]))
     x0 = np.tile(pb["x_opts"], (C // 5 + 1, 1))[:C]
-    out = {}
-    for name, sampler, kw, scale0, burn, N, thin in (("mh", E.SAMPLER_MH, {}, 0.128, 2000, 6000, 20),
-                                                     ("cw", E.SAMPLER_CWMH, {"cw_scale": 1.5 * sd}, 0.1, 10000, 30000, 100)):
-        eng = helpers.engine(pb, C, 1)
-        eng.set_sampler(sampler, **kw)
-        eng.init_chains(x0, scale0=scale0, seed=123)
-        eng.run(burn, 0, burn, keep_samples=False)
-        smp, _ = eng.run(N, 0, thin)
-        S = smp.cpu().numpy().transpose(1, 0, 2).reshape(3, -1)
-        out[name] = (S.mean(axis=1), S.std(axis=1))
-        eng.close()
-    assert np.all(np.abs(out["cw"][0] - out["mh"][0]) < 0.15 * out["mh"][1]), out
-    assert np.all(np.abs(out["cw"][1] / out["mh"][1] - 1.0) < 0.10), out
+    eng = helpers.engine(pb, C, 1)
+    eng.init_chains(x0, scale0=0.128, seed=123)
+    eng.run(2000, 0, 2000, keep_samples=False)
+    smp, _ = eng.run(6000, 0, 20)
+    S = smp.cpu().numpy().transpose(1, 0, 2).reshape(3, -1)
+    mh = (S.mean(axis=1), S.std(axis=1))
+    start = eng.state()["x"].t().contiguous().cpu().numpy()          # [C, 3]: one posterior draw per chain
+    eng.close()
+    N = 40000
+    eng = helpers.engine(pb, C, 1)
+    eng.set_sampler(E.SAMPLER_CWMH, cw_scale=0.1 * sd)
+    eng.init_chains(start, scale0=0.1, seed=321)
+    smp, _ = eng.run(N, int(0.012 * N), 200)                          # cuqi CWMH adaptation window
+    X = smp.cpu().numpy()                                             # [200, 3, C]
+    acc = eng.state()["accept_count"].double().mean().item() / (3 * N)
+    eng.close()
+    assert 0.15 < acc < 0.45, acc                                     # adapted towards 0.21/3 + 0.23 = 0.30
+    end = X[-1].T
+    forgot = [abs(np.corrcoef(start[:, p], end[:, p])[0, 1]) for p in range(3)]
+    assert max(forgot) < 0.5, forgot                                  # the chains moved away from their starting draws
+    Scw = X[100:].transpose(1, 0, 2).reshape(3, -1)                   # second half of the run
+    cw = (Scw.mean(axis=1), Scw.std(axis=1))
+    assert np.all(np.abs(cw[0] - mh[0]) < 0.15 * mh[1]), (cw, mh)
+    assert np.all(np.abs(cw[1] / mh[1] - 1.0) < 0.10), (cw, mh)
 
 
 # ----------------------------------------------------------------------------- (iv) Q-factor notebook statistics
