@@ -216,6 +216,9 @@ class Samples:
         raise NotImplementedError("plotting is out of scope (matplotlib/arviz not in this image)")
 
 
+_ACOV_MAX_DRAWS = 20480        # mems_chain_autocov: draws of one (half-)chain that fit in shared memory
+
+
 class BatchedSamples:
     """C chains at once: ``.samples`` is ``(C, dim, Ns)``; indexing yields per-chain :class:`Samples`.
 
@@ -304,6 +307,13 @@ class BatchedSamples:
         C, P, Ns = self.shape
         if on_device is None:
             on_device = self._dev is not None or C * Ns > 2_000_000
+        if on_device and Ns // 2 > _ACOV_MAX_DRAWS:
+            # the device autocovariance kernel stages a half-chain in shared memory (<= 20480 draws): longer chains go to the
+            # host estimator when that is affordable, otherwise they are thinned to the limit first (ESS of the kept draws)
+            if C * Ns <= 50_000_000:
+                on_device = False
+            else:
+                return self.burnthin(0, (Ns // 2) // _ACOV_MAX_DRAWS + 1).compute_ess(on_device=True, device=device)
         if not on_device:
             return np.array([diagnostics.ess_bulk(self.samples[:, j, :]) for j in range(P)])
         from . import diagnostics_device
@@ -351,7 +361,8 @@ class MH:
             raise ValueError("MH proposal must be a symmetric (zero-mean Gaussian) distribution")
         self.proposal = proposal
         self.scale = scale
-        self.x0 = np.ones(self.dim) if x0 is None else np.asarray(x0, np.float64)
+        # x0: [P] (one chain, cuqi), [C, P] (C chains at once); a torch tensor (e.g. pinned host memory) is taken as it is
+        self.x0 = np.ones(self.dim) if x0 is None else (x0 if hasattr(x0, "is_cuda") else np.asarray(x0, np.float64))
         self.seed, self.path, self.device, self.chain_id0 = seed, path, device, chain_id0
         fwd = target.model.forward_func
         if not hasattr(fwd, "spec"):

@@ -22,8 +22,9 @@ def surrogate_spec(data_processor, nn_model) -> SurrogateSpec:
                          scaler_scale=np.asarray(sc.scale_, np.float64))
 
 
-def create_forward_model_function(data_processor, nn_model, path: int = PATH_FP32, device: int = 0):
-    """``x[P] -> float32[T]`` like the reference closure; also accepts ``x[n,P] -> [n,T]``.
+def create_forward_model_function(data_processor, nn_model, path: int = PATH_TC, device: int = 0):
+    """``x[P] -> float32[T]`` like the reference closure; also accepts ``x[n,P] -> [n,T]``.  Evaluated on the product
+    (tensor-core) path unless ``path=PATH_FP32`` asks for the FP32 check path.
 
     The returned callable exposes ``.spec`` (weights, scaler constants, time grid) so that the
     batched sampler can find the surrogate without introspecting a closure.

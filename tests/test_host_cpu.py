@@ -174,11 +174,19 @@ def test_sensitivity_fixture_and_push_forward_math():
 def test_bench_reference_arm_pieces_run_on_cpu():
     """bench.py --impl reference times this function on every host core: keep it importable and sane without a GPU."""
     import bench
-    dt = bench._cpu_chain(("geometric", 150, 40, 0))
+    dt = bench._cpu_chain((150, 40, 0))
     assert 0.0 < dt < 30.0
     assert bench.flop_per_row(3) == 41600 and bench.flop_per_row(4) == 41728
     class A:   # noqa: E701
-        workload, chains, inner, thin, path = "geometric_4096", 4096, 256, 64, "tc"
-    assert bench.measured_traffic(A) > 100000
-    A.chains = 1024
-    assert bench.measured_traffic(A) is None
+        workload, chains, inner, thin, path, time_points = "geometric_4096", 4096, 256, 64, "tc", 150
+    traffic, src = bench.measured_traffic(A, 4096)
+    assert traffic > 100000 and src.endswith(".json")
+    assert bench.measured_traffic(A, 1024) == (None, None)
+    assert bench.chains_of(A, 8) == (8 * 4096, 4096)
+    A.workload, A.chains = "sweep_1M", 0
+    assert bench.chains_of(A, 8) == (1 << 20, 1 << 17)
+    cfg = bench.workload_config(A, 4)
+    assert cfg["workload"] == "sweep_1M" and cfg["chains_total"] == 1 << 20 and cfg["chains_per_gpu"] == 1 << 18
+    # the bench rebuilds the reference-shaped objects from the package's fixtures, not from the test tree
+    src = open(bench.__file__).read()
+    assert "helpers" not in src and "os.path.join(ROOT, \"tests\")" not in src
