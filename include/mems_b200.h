@@ -192,6 +192,27 @@ int  mems_chain_moments(int32_t device, const double* samples_dev, int32_t n_kee
 int  mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep, int32_t n_params,
                         int32_t n_chains, int32_t max_lag, double* out_dev, void* stream);
 
+/* Rank-normalised diagnostics (arviz defaults behind Samples.compute_ess / compute_rhat: bulk ESS and rank-normalised
+ * split R-hat; call sites tests/Xaccelerometer_geometric/identification.ipynb:308,311), three device steps:
+ *
+ * mems_sort_f64: ascending in-place sort of n f64 keys.  keys_dev must have room for mems_sort_capacity(n) doubles
+ * (the network works on a power-of-two length; the tail is scratch).  Deterministic.
+ *
+ * mems_rank_normalize: for each of the n values x_dev[i], the tie-averaged 1-based rank r among the n_pool sorted
+ * values sorted_dev (the pooled draws of every chain -- of every GPU when the pool was gathered), then
+ * z_dev[i] = Phi^-1((r - 3/8)/(n_pool + 1/4)).  x_dev and z_dev may alias.
+ *
+ * mems_ess_geyer: effective sample size from autocovariance sums in the layout mems_chain_autocov writes
+ * (acov_dev [n_params][max_lag + 2], SUMS over n_chains chains of n_draws draws, possibly all-reduced over GPUs):
+ * Geyer's initial-positive + initial-monotone truncation.  ess_out_dev [n_params] f64; truncated_out_dev [n_params]
+ * i32 = 1 when the sequence had not turned negative by max_lag. */
+int64_t mems_sort_capacity(int64_t n);
+int  mems_sort_f64(int32_t device, double* keys_dev, int64_t n, void* stream);
+int  mems_rank_normalize(int32_t device, const double* sorted_dev, int64_t n_pool, const double* x_dev, int64_t n,
+                         double* z_dev, void* stream);
+int  mems_ess_geyer(int32_t device, const double* acov_dev, int32_t n_params, int32_t max_lag, int64_t n_draws,
+                    int64_t n_chains, double* ess_out_dev, int32_t* truncated_out_dev, void* stream);
+
 /* Batched bounded least-squares fit of the surrogate to observed traces: n independent starts advance together.
  * Replaces least_squares_optimization (src/InverseProblems/utils.py:83-93: scipy least_squares with
  * jac='3-point' and bounds, then inv(J^T J)), which the notebooks call once per start

@@ -25,6 +25,7 @@ EXPORTS = [
     "mems_last_error", "mems_version", "mems_create", "mems_destroy", "mems_set_weights",
     "mems_set_problem", "mems_forward", "mems_init_chains", "mems_run", "mems_run_explicit",
     "mems_draw", "mems_get_state", "mems_get_aux", "mems_set_sampler", "mems_mlp_forward", "mems_chain_moments", "mems_launch_count", "mems_rows_evaluated", "mems_lsq", "mems_chain_autocov", "mems_set_coarse_fft",
+    "mems_sort_capacity", "mems_sort_f64", "mems_rank_normalize", "mems_ess_geyer",
 ]
 
 
@@ -76,6 +77,11 @@ def lib():
     L.mems_lsq.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, dbl, dbl, dbl, vp, vp, vp, vp, vp]
     L.mems_chain_autocov.argtypes = [i32, vp, i32, i32, i32, i32, vp, vp]
     L.mems_set_coarse_fft.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), vp, vp]
+    L.mems_sort_capacity.argtypes = [i64]
+    L.mems_sort_capacity.restype = i64
+    L.mems_sort_f64.argtypes = [i32, vp, i64, vp]
+    L.mems_rank_normalize.argtypes = [i32, vp, i64, vp, i64, vp, vp]
+    L.mems_ess_geyer.argtypes = [i32, vp, i32, i32, i64, i64, vp, vp, vp]
     _lib = L
     return L
 

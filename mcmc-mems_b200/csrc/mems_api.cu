@@ -19,6 +19,11 @@ int mems_lsq_run(const MemsLaunchCtx& ctx, bool use_tc, const double* x0_dev, in
                  double* x_out, double* cov_out, double* cost_out, int* iters_out);
 size_t mems_acov_workspace_bytes(int n_keep, int P, int C, int L);
 int mems_acov_launch(const double* samples, int n_keep, int P, int C, int L, void* workspace, double* out, cudaStream_t st);
+size_t mems_sort_padded(size_t n);
+int mems_sort_launch(double* keys, size_t n, int sm_count, cudaStream_t st);
+int mems_rank_normalize_launch(const double* sorted, size_t M, const double* x, size_t n, double* z, int sm_count, cudaStream_t st);
+int mems_geyer_launch(const double* acov, int P, int L, long long n_draws, double n_chains, double* rho_scratch, double* out,
+                      int* trunc, cudaStream_t st);
 size_t mems_tc_wimg_bytes();
 void mems_tc_build_wimg(const MemsProblem& pb, void* host_img);
 
@@ -604,6 +609,65 @@ int mems_chain_autocov(int32_t device, const double* samples_dev, int32_t n_keep
     const int e = mems_acov_launch(samples_dev, n_keep, n_params, n_chains, max_lag, ws, out_dev, st);
     cudaFreeAsync(ws, st);
     if (e != 0) return fail(MEMS_E_CUDA, "autocovariance launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+namespace {
+int device_sm_count(int device, int* sm_count) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MEMS_E_UNSUPPORTED, "no CUDA device; this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(MEMS_E_INVALID, "device %d out of range", device);
+    CUDA_TRY(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
+    return MEMS_OK;
+}
+}  // namespace
+
+int64_t mems_sort_capacity(int64_t n) { return n < 0 ? 0 : (int64_t)mems_sort_padded((size_t)n); }
+
+int mems_sort_f64(int32_t device, double* keys_dev, int64_t n, void* stream) {
+    if (n < 0) return fail(MEMS_E_INVALID, "n < 0");
+    if (n <= 1) return MEMS_OK;
+    if (!keys_dev) return fail(MEMS_E_INVALID, "null argument");
+    int sms = 0;
+    const int rc = device_sm_count(device, &sms);
+    if (rc != MEMS_OK) return rc;
+    DEVICE_SCOPE(device);
+    const int e = mems_sort_launch(keys_dev, (size_t)n, sms, reinterpret_cast<cudaStream_t>(stream));
+    if (e != 0) return fail(MEMS_E_CUDA, "sort launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+int mems_rank_normalize(int32_t device, const double* sorted_dev, int64_t n_pool, const double* x_dev, int64_t n, double* z_dev,
+                        void* stream) {
+    if (n < 0 || n_pool < 1) return fail(MEMS_E_INVALID, "need n >= 0 and n_pool >= 1");
+    if (n == 0) return MEMS_OK;
+    if (!sorted_dev || !x_dev || !z_dev) return fail(MEMS_E_INVALID, "null argument");
+    int sms = 0;
+    const int rc = device_sm_count(device, &sms);
+    if (rc != MEMS_OK) return rc;
+    DEVICE_SCOPE(device);
+    const int e = mems_rank_normalize_launch(sorted_dev, (size_t)n_pool, x_dev, (size_t)n, z_dev, sms, reinterpret_cast<cudaStream_t>(stream));
+    if (e != 0) return fail(MEMS_E_CUDA, "rank_normalize launch failed: %s", cudaGetErrorString((cudaError_t)e));
+    return MEMS_OK;
+}
+
+int mems_ess_geyer(int32_t device, const double* acov_dev, int32_t n_params, int32_t max_lag, int64_t n_draws, int64_t n_chains,
+                   double* ess_out_dev, int32_t* truncated_out_dev, void* stream) {
+    if (!acov_dev || !ess_out_dev || !truncated_out_dev) return fail(MEMS_E_INVALID, "null argument");
+    if (n_params < 1 || max_lag < 2 || n_draws < 4 || n_chains < 1)
+        return fail(MEMS_E_INVALID, "need n_params >= 1, max_lag >= 2, n_draws >= 4, n_chains >= 1");
+    int sms = 0;
+    const int rc = device_sm_count(device, &sms);
+    if (rc != MEMS_OK) return rc;
+    DEVICE_SCOPE(device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    double* rho = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&rho), sizeof(double) * (size_t)n_params * ((size_t)max_lag + 2), st));
+    const int e = mems_geyer_launch(acov_dev, n_params, max_lag, (long long)n_draws, (double)n_chains, rho, ess_out_dev,
+                                    truncated_out_dev, st);
+    cudaFreeAsync(rho, st);
+    if (e != 0) return fail(MEMS_E_CUDA, "geyer launch failed: %s", cudaGetErrorString((cudaError_t)e));
     return MEMS_OK;
 }
 

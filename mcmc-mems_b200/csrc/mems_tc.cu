@@ -61,6 +61,9 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
     uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S
+    const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
+    const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
+    const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
     for (;;) {
         mbar_wait(&gs.bar_S, (ph >> 4) & 1u);
         ph ^= 16u;
@@ -74,16 +77,16 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                 for (int s = 0; s < GSLOT; ++s) {
                     if (pair * 2 + s < n_tiles) {
                         if (layer == 0) {
-                            mbar_wait(&gs.bar_At[s], (ph >> (2 + s)) & 1u);
+                            mbar_wait_a(aAt + 8 * s, (ph >> (2 + s)) & 1u);
                             ph ^= (4u << s);
                         } else {
-                            mbar_wait(&gs.bar_Ah[s], (ph >> s) & 1u);
+                            mbar_wait_a(aAh + 8 * s, (ph >> s) & 1u);
                             ph ^= (1u << s);
                         }
                         tc_fence_after();
                         if (elect_one()) {
                             issue_layer(wimg, base + s * 128, layer);
-                            umma_commit(&gs.bar_Dh[s]);
+                            umma_commit_a(aDh + 8 * s);
                         }
                         __syncwarp();
                     }
@@ -153,6 +156,9 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
         constexpr int NCOL = 64 / NH;                 // accumulator columns per thread
         const int h = gt >> 7;                        // column half
+        const uint32_t aDh = keep_in_register(smem_u32(&gs.bar_Dh[0]));
+        const uint32_t aAh = aDh - (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_Ah));
+        const uint32_t aX = aDh + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_Dh));
         for (int pair = 0; pair < n_pairs; ++pair) {
 #pragma unroll 1
             for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
@@ -160,7 +166,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                 for (int s = 0; s < GSLOT; ++s) {
                     if (pair * 2 + s < n_tiles) {
                         const uint32_t tD = tD0 + s * 128;
-                        mbar_wait(&gs.bar_Dh[s], (ph >> s) & 1u);
+                        mbar_wait_a(aDh + 8 * s, (ph >> s) & 1u);
                         ph ^= (1u << s);
                         tc_fence_after();
                         // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain
@@ -178,7 +184,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                             }
                             tc_wait_st();
                             tc_fence_before();
-                            mbar_arrive(&gs.bar_Ah[s]);
+                            mbar_arrive_a(aAh + 8 * s);
                         } else {                               // last tanh layer . output weights: partial dot to the tail warps
                             uint64_t acc = pk(0.0f, 0.0f);
 #pragma unroll
@@ -194,7 +200,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                             upk(acc, oa, ob);
                             gs.xchg[s][h][row] = oa + ob;
                             tc_fence_before();                 // the accumulator has been read: the slot may be restaged
-                            mbar_arrive(&gs.bar_X[s]);         // release: the store above is visible to the tail warps
+                            mbar_arrive_a(aX + 8 * s);         // release: the store above is visible to the tail warps
                         }
                     }
                 }
@@ -206,6 +212,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         const int sub = row / nce;
         const int j = compact ? (int)gs.map[jc] : jc; // batch-local chain index
         const bool chain_live = (sub < tpt) && (compact || jc < ncv);
+        const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
+        const uint32_t aX = aAt + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_At));
         uint32_t a1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
@@ -233,7 +241,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             tmem_st16(tD0 + s * 128 + 64, a1);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(&gs.bar_At[s]);
+            mbar_arrive_a(aAt + 8 * s);
         };
 #pragma unroll
         for (int s = 0; s < GSLOT; ++s)
@@ -245,7 +253,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             for (int s = 0; s < GSLOT; ++s) {
                 const int tile = pair * 2 + s;
                 if (tile < n_tiles) {
-                    mbar_wait(&gs.bar_X[s], (ph >> s) & 1u);
+                    mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
                     ph ^= (1u << s);
                     tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
                     const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + sm.b7;

@@ -144,6 +144,31 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// The same on a precomputed shared-window address (hot loops: the generic -> shared conversion of a barrier that lives in
+// the dynamic shared-memory struct otherwise costs an S2R + LEA in front of every wait and arrive).
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t v) {      // stops the compiler from recomputing v at every use
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    if (mbar_try_a(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_a(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -194,6 +219,10 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 __device__ __forceinline__ void umma_commit(void* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {

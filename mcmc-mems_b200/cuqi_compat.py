@@ -300,33 +300,37 @@ class BatchedSamples:
 
     _device_samples = device_samples
 
-    def compute_ess(self, on_device: Optional[bool] = None, device: int = 0):
+    def compute_ess(self, on_device: Optional[bool] = None, device: int = 0, across_ranks: bool = False):
         """Bulk effective sample size per parameter over all chains (arviz's default, rank-normalised).  Large batches,
-        device-resident draws (or ``on_device=True``) are ranked and reduced on the GPU (``diagnostics_device.ess_bulk``):
-        shipping 10^6 chains to arviz is the bottleneck the device path removes."""
+        device-resident draws (or ``on_device=True``) are ranked and reduced on the GPU by the library's own kernels
+        (``diagnostics_device.ess_bulk``): shipping 10^6 chains to arviz is the bottleneck the device path removes
+        (SURVEY.md 8f1).  ``across_ranks=True``: this object holds one shard of a ``torch.distributed`` run and the
+        estimate is over the chains of every rank (global ranks; same number on any GPU count)."""
         C, P, Ns = self.shape
         if on_device is None:
-            on_device = self._dev is not None or C * Ns > 2_000_000
+            on_device = across_ranks or self._dev is not None or C * Ns > 2_000_000
         if on_device and Ns // 2 > _ACOV_MAX_DRAWS:
             # the device autocovariance kernel stages a half-chain in shared memory (<= 20480 draws): longer chains go to the
             # host estimator when that is affordable, otherwise they are thinned to the limit first (ESS of the kept draws)
-            if C * Ns <= 50_000_000:
+            if C * Ns <= 50_000_000 and not across_ranks:
                 on_device = False
             else:
-                return self.burnthin(0, (Ns // 2) // _ACOV_MAX_DRAWS + 1).compute_ess(on_device=True, device=device)
+                return self.burnthin(0, (Ns // 2) // _ACOV_MAX_DRAWS + 1).compute_ess(on_device=True, device=device,
+                                                                                        across_ranks=across_ranks)
         if not on_device:
             return np.array([diagnostics.ess_bulk(self.samples[:, j, :]) for j in range(P)])
         from . import diagnostics_device
-        return diagnostics_device.ess_bulk(self.device_samples(device))
+        return diagnostics_device.ess_bulk(self.device_samples(device), group=None if across_ranks else False)
 
-    def compute_rhat(self, on_device: Optional[bool] = None, device: int = 0):
+    def compute_rhat(self, on_device: Optional[bool] = None, device: int = 0, across_ranks: bool = False):
+        """Rank-normalised split R-hat per parameter over all chains (arviz's default); see :meth:`compute_ess`."""
         C, P, Ns = self.shape
         if on_device is None:
-            on_device = self._dev is not None or C * Ns > 2_000_000
+            on_device = across_ranks or self._dev is not None or C * Ns > 2_000_000
         if not on_device:
             return np.array([diagnostics.rhat_rank(self.samples[:, j, :]) for j in range(P)])
         from . import diagnostics_device
-        return diagnostics_device.rhat_rank(self.device_samples(device))
+        return diagnostics_device.rhat_rank(self.device_samples(device), group=None if across_ranks else False)
 
 
 # -- sampler ---------------------------------------------------------------------------------
