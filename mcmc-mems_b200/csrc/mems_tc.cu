@@ -52,12 +52,13 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
     }
 }
 
-// MMA issuer warp of one group (all 32 lanes run the loop convergently; one elected lane issues): for every
-// surrogate pass the group announces (ctrl_tiles via bar_S) it serves the group's two slots in the fixed order
-// the epilogue warps produce them; ctrl_tiles < 0 ends the loop.  `g` must be warp-uniform.
+// MMA issuer warp (all 32 lanes run the loop convergently; one elected lane issues).  It serves `nslot` slots of group g
+// starting at slot0 (one slot with MEMS_ISSUER_PER_SLOT, else both) in the fixed order the epilogue warps produce them: for every
+// surrogate pass the group announces (ctrl_tiles via bar_S) tiles slot, slot + GSLOT, ...; ctrl_tiles < 0 ends the loop.
 // Per tile: layer 0 waits for the tail warps' layer-1 operand, layers 1..5 for the hidden warps' A operands; every
-// accumulator goes to the hidden warps (bar_Dh).
-__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g) {
+// accumulator goes to the hidden warps (bar_Dh).  g, slot0 must be warp-uniform.
+template <int NSLOT>
+__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g, int slot0) {
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
     uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S
@@ -65,17 +66,17 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
     const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
     const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
     for (;;) {
-        mbar_wait(&gs.bar_S, (ph >> 4) & 1u);
+        mbar_wait(&gs.bar_S[slot0], (ph >> 4) & 1u);
         ph ^= 16u;
         const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
         if (n_tiles < 0) break;
-        const int n_pairs = (n_tiles + 1) >> 1;
-        for (int pair = 0; pair < n_pairs; ++pair) {
+        for (int t0 = 0; t0 < n_tiles; t0 += GSLOT) {
 #pragma unroll 1
             for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
-                for (int s = 0; s < GSLOT; ++s) {
-                    if (pair * 2 + s < n_tiles) {
+                for (int k = 0; k < NSLOT; ++k) {
+                    const int s = slot0 + k;
+                    if (t0 + s < n_tiles) {
                         if (layer == 0) {
                             mbar_wait_a(aAt + 8 * s, (ph >> (2 + s)) & 1u);
                             ph ^= (4u << s);
@@ -93,6 +94,18 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                 }
             }
         }
+    }
+}
+
+// Tell the group's MMA issuer(s) how many tiles follow (n_tiles < 0: no more work).  One thread of the group.
+__device__ __forceinline__ void announce_tiles(GroupSmem& gs, int n_tiles) {
+    *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
+    if (MEMS_ISSUER_PER_SLOT) {
+#pragma unroll
+        for (int s = 0; s < GSLOT; ++s)
+            if (n_tiles < 0 || s < n_tiles) mbar_arrive(&gs.bar_S[s]);     // an issuer without a tile in this pass is not woken
+    } else {
+        mbar_arrive(&gs.bar_S[0]);
     }
 }
 
@@ -147,10 +160,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
     const int n_pairs = (n_tiles + 1) >> 1;
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
-    if (gt == 0) {                                    // tell the group's MMA issuer how many tiles follow
-        *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
-        mbar_arrive(&gs.bar_S);
-    }
+    if (gt == 0) announce_tiles(gs, n_tiles);
 
     if (!is_tail) {
         // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
@@ -326,13 +336,17 @@ __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt,
 // thread -> (group, index within the group's epilogue threads); issuer warps get gt = -1
 //   tid <  NGROUP*HTHREADS                : hidden threads, group = tid / HTHREADS, gt = tid % HTHREADS
 //   tid <  NWORKER                        : tail threads,   group = (tid - 512) / TTHREADS, gt = HTHREADS + row
-//   else                                  : MMA issuer warp of group (tid - NWORKER) / 32
+//   else                                  : MMA issuer warps; gt = -1 - (first slot served); one warp per (group, slot) or per group
 // (warp % 4 is the TMEM lane quarter of row = 32 * (warp % 4) + lane in both worker kinds)
 __device__ __forceinline__ void my_role(int& g, int& gt) {
     const int tid = threadIdx.x;
     if (tid < NGROUP * HTHREADS) { g = tid / HTHREADS; gt = tid % HTHREADS; }
     else if (tid < NWORKER) { g = (tid - NGROUP * HTHREADS) / TTHREADS; gt = HTHREADS + (tid - NGROUP * HTHREADS) % TTHREADS; }
-    else { g = (tid - NWORKER) >> 5; gt = -1; }
+    else {
+        const int iw = (tid - NWORKER) >> 5;
+        if (MEMS_ISSUER_PER_SLOT) { g = iw / GSLOT; gt = -1 - iw % GSLOT; }
+        else { g = iw; gt = -1; }
+    }
 }
 
 // Common prologue: barriers, TMEM, weight image (bulk TMA), y_obs / time columns.
@@ -347,7 +361,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
                 mbar_init(&sm.grp[g].bar_Dh[s], 1);
                 mbar_init(&sm.grp[g].bar_X[s], HTHREADS);
             }
-            mbar_init(&sm.grp[g].bar_S, 1);
+            for (int s = 0; s < GSLOT; ++s) mbar_init(&sm.grp[g].bar_S[s], 1);
             sm.grp[g].ctrl_tiles = 0;
         }
         mbar_init(&sm.bar_w, 1);
@@ -401,7 +415,8 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
 
     if (gt < 0) {
         const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
-        mma_issuer_loop(sm, sm.grp[gw], gw);
+        const int sw = __shfl_sync(0xffffffffu, -1 - gt, 0);             // and first slot
+        mma_issuer_loop<MEMS_ISSUER_PER_SLOT ? 1 : GSLOT>(sm, sm.grp[gw], gw, sw);
     } else {
         uint32_t ph = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
@@ -435,10 +450,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
             batch_store(gs.cb, ch, P, ra.mode, c0, gt, ncv);
         }
         group_bar_sync(g);
-        if (gt == 0) {
-            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
-            mbar_arrive(&gs.bar_S);
-        }
+        if (gt == 0) announce_tiles(gs, -1);
     }
     tc_epilogue_free(sm);
 }
@@ -463,7 +475,8 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
 
     if (gt < 0) {
         const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
-        mma_issuer_loop(sm, sm.grp[gw], gw);
+        const int sw = __shfl_sync(0xffffffffu, -1 - gt, 0);             // and first slot
+        mma_issuer_loop<MEMS_ISSUER_PER_SLOT ? 1 : GSLOT>(sm, sm.grp[gw], gw, sw);
     } else {
         uint32_t ph = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
@@ -490,10 +503,7 @@ tc_forward_kernel(const MemsProblem* __restrict__ pbp, const double* __restrict_
             }
         }
         group_bar_sync(g);
-        if (gt == 0) {
-            *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = -1;
-            mbar_arrive(&gs.bar_S);
-        }
+        if (gt == 0) announce_tiles(gs, -1);
     }
     tc_epilogue_free(sm);
 }

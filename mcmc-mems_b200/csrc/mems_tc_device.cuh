@@ -44,7 +44,9 @@ namespace {
 //                               bookkeeping.  In round 1 the hidden warps did this too, serially (10 % of their time,
 //                               profiles/r02_*), and the XU pipe idled meanwhile.  (Giving the tail warps the last tanh
 //                               layer as well was measured: its latency stalls the slot, 38.9 M vs this layout);
-//   MMA issuer   (1 per group)  32 lanes converged, one elected lane issues tcgen05.mma / commit.
+//   MMA issuer   (1 per slot)   32 lanes converged, one elected lane issues tcgen05.mma / commit.  Four issuer warps put one on
+//                               every SM sub-partition: with one per group the two sub-partitions that hosted them lost issue
+//                               slots to their polling and their TMEM lane quarters lagged behind (profiles/r02_*).
 // Hand-offs are mbarriers (tail -> issuer -> hidden -> issuer ... -> tail); groups never synchronise with each other, so
 // one group's accept/reject section overlaps the other group's tensor work.  The first min(n_chains, 128) hidden
 // threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
@@ -55,7 +57,11 @@ constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
 constexpr int TTHREADS = 128;                  // tail threads per group
 constexpr int GTHREADS = HTHREADS + TTHREADS;  // 384: the threads of a group that meet at group barriers
 constexpr int NWORKER = NGROUP * GTHREADS;     // 768
-constexpr int NTHREADS = NWORKER + 32 * NGROUP;  // + one MMA issuer warp per group = 832
+#ifndef MEMS_ISSUER_PER_SLOT
+#define MEMS_ISSUER_PER_SLOT 1                 // 1: one MMA-issuer warp per (group, slot) -> one per SM sub-partition; 0: one per group
+#endif
+constexpr int NISSUER = MEMS_ISSUER_PER_SLOT ? NGROUP * GSLOT : NGROUP;   // MMA-issuer warps
+constexpr int NTHREADS = NWORKER + 32 * NISSUER; // 896 (832 with one issuer warp per group)
 constexpr int BLK = 8192;             // one [64 rows][64 halves] 128B-swizzled operand block
 constexpr int BLK_B1 = 0;             // layer-1 B operand
 constexpr int BLK_WHI = 1;            // 5 blocks
@@ -79,7 +85,8 @@ struct GroupSmem {
     unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of the slot is complete
     unsigned long long bar_X[GSLOT];   // hidden -> tail warps: partial output-layer dots of the slot's tile are in xchg
     float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves
-    unsigned long long bar_S;          // group -> MMA issuer: ctrl_tiles of the next pass is valid
+    unsigned long long bar_S[GSLOT];   // group -> MMA issuer of the slot: ctrl_tiles of the next pass is valid (signalled only when
+                                       // the pass has a tile for that slot, or to end: every signalled phase is consumed before the next)
     int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
