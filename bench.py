@@ -19,7 +19,8 @@ Reported
              ``BatchedSamples`` -> ``.samples`` -- with x0 in pinned host memory and the kept draws read back to pinned
              host memory inside the timed region
   end_of_run the collectives of the sweep, timed on NCCL: R-hat / posterior-moment all-reduces, the all-gather of the kept
-             draws, the ESS reduction -- and their share of a full 10 000-update run
+             draws, the ESS reduction, the rank-normalised (arviz-default) R-hat and bulk ESS over all ranks -- and their
+             share of a full 10 000-update run
   roofline   tensor-core: algorithmic FLOPs of the surrogate rows actually evaluated (device counter) / launch time
 
 Prints ONE JSON line on rank 0.
@@ -391,6 +392,11 @@ def run_ours(args):
     gather_bytes = int(gathered.numel() * 8)
     gathered_shape = list(gathered.shape)
     del gathered
+    # arviz-default (rank-normalised) R-hat and bulk ESS over every chain of every rank: all-gather of the pool, the library's
+    # own sort / rank / quantile / Geyer kernels on each GPU, all-reduces of the moments and lag sums
+    from mcmc_mems_b200 import diagnostics_device as DD
+    rank_rhat, ms_rank_rhat = timed(lambda: DD.rhat_rank(post_smp))
+    rank_ess, ms_rank_ess = timed(lambda: DD.ess_bulk(post_smp, max_lag=post_keep // 2))
 
     # ---- the 4096-chains-per-GPU configuration of BASELINE.json configs[1], in the same run
     second = None
@@ -442,15 +448,18 @@ def run_ours(args):
                          "sample_writeback_gbs": (S // thin) * 3 * C * 8 / t_launch / 1e9,
                          "flop_per_chain_step": flop_step},
             "end_of_run": {"all_reduce_ms": ms_allreduce, "all_gather_ms": ms_gather, "ess_ms": ms_ess,
+                           "rank_rhat_ms": ms_rank_rhat, "rank_ess_ms": ms_rank_ess,
                            "all_gather_bytes": gather_bytes, "gathered_shape": gathered_shape,
                            "kept_draws_per_chain": post_keep, "backend": "nccl" if world > 1 else "none (1 rank)",
                            "full_run_ms_at_measured_rate": full_run_ms,
-                           "share_of_full_run": (ms_allreduce + ms_gather + ms_ess) / full_run_ms},
+                           "share_of_full_run": (ms_allreduce + ms_gather + ms_ess + ms_rank_rhat + ms_rank_ess) / full_run_ms},
             "clocks": clk,
             "wall_s_timed_region": m["wall"],
             "check": {"split_rhat": [float(v) for v in rhat.cpu()], "post_mean": [float(v) for v in mean.cpu()],
                       "post_std": [float(v) for v in std.cpu()], "accept_rate": acc_rate_chain,
-                      "ess_thinned_draws": [float(v) for v in ess], "kept_draws": int(post_keep * total)},
+                      "ess_thinned_draws": [float(v) for v in ess], "kept_draws": int(post_keep * total),
+                      "rank_normalised_split_rhat": [float(v) for v in rank_rhat],
+                      "bulk_ess": [float(v) for v in rank_ess]},
         }
         if second is not None:
             line["geometric_4096"] = second

@@ -263,7 +263,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             for (int s = 0; s < GSLOT; ++s) {
                 const int tile = pair * 2 + s;
                 if (tile < n_tiles) {
-                    mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
+                    if (MEMS_TAIL_WAIT_HINT_NS > 0) mbar_wait_hint_a(aX + 8 * s, (ph >> s) & 1u, MEMS_TAIL_WAIT_HINT_NS);
+                    else mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
                     ph ^= (1u << s);
                     tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
                     const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + sm.b7;

@@ -15,6 +15,9 @@
 #ifndef MEMS_TRYWAIT_HINT
 #define MEMS_TRYWAIT_HINT 0
 #endif
+#ifndef MEMS_TAIL_WAIT_HINT_NS
+#define MEMS_TAIL_WAIT_HINT_NS 0   // > 0: suspend-time hint of the tail warps' wait for a tile's output dots
+#endif
 #ifndef MEMS_EX2_MIX
 #define MEMS_EX2_MIX 0         // (round-1 arithmetic, micro-benchmarks only) share of exponentials on the FMA pipe
 #endif
@@ -143,12 +146,17 @@ __device__ __forceinline__ bool mbar_try(void* bar, uint32_t parity) {
 #endif
     return ok != 0;
 }
-// Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.
+// Blocking wait with a watchdog: a protocol bug must trap, never hang the GPU.  try_wait suspends the warp for a
+// hardware-defined slice (~80 cycles measured) before it returns false; the watchdog counts those slices (2^26 of them is
+// several seconds) instead of reading the clock, which halves the instructions a waiting warp issues -- on a power-capped GPU
+// the polling of idle warps competes with the epilogue for both issue slots and watts.
+#ifndef MEMS_WATCHDOG_SPINS
+#define MEMS_WATCHDOG_SPINS (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-    if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > MEMS_WATCHDOG_SPINS) __trap();
     }
 }
 // The same on a precomputed shared-window address (hot loops: the generic -> shared conversion of a barrier that lives in
@@ -170,10 +178,26 @@ __device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
-    if (mbar_try_a(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_a(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > MEMS_WATCHDOG_SPINS) __trap();
+    }
+}
+// The same for waiters that are off the critical path most of the time (tail warps between tiles): a suspend-time hint
+// lets the hardware park the warp longer between polls.
+__device__ __forceinline__ bool mbar_try_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint_a(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_hint_a(bar, parity, hint_ns)) {
+        if (++spins > MEMS_WATCHDOG_SPINS) __trap();
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
