@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -25,6 +26,9 @@ int mems_rank_normalize_launch(const double* sorted, size_t M, const double* x, 
 int mems_geyer_launch(const double* acov, int P, int L, long long n_draws, double n_chains, double* rho_scratch, double* out,
                       int* trunc, cudaStream_t st);
 size_t mems_tc_wimg_bytes();
+size_t mems_tc_coarse_wimg_bytes();
+bool mems_tc_coarse_fits(int T, size_t smem_optin);
+void mems_tc_build_coarse_wimg(MemsCoarse& cm, int P, void* host_img);
 void mems_tc_build_wimg(const MemsProblem& pb, void* host_img);
 
 namespace {
@@ -78,6 +82,8 @@ struct MemsHandle_ {
     void* dev_wimg = nullptr;
     MemsCoarse* dev_coarse = nullptr;      // FFT coarse surrogate of delayed acceptance (device copy)
     MemsCoarse* host_coarse = nullptr;
+    void* dev_coarse_wimg = nullptr;       // tensor-core path: operand image of the coarse surrogate (global memory, streamed)
+    size_t smem_optin = 0;
     bool have_coarse = false, use_coarse = false;
     std::vector<double> host_yobs;
     MemsChains chains;
@@ -176,6 +182,7 @@ int mems_create(const MemsConfig* cfg, mems_handle_t* out) {
     if (!h) return fail(MEMS_E_INVALID, "out of host memory");
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&h->host_pb, 0, sizeof(MemsProblem));
     h->host_pb.c.P = cfg->n_params;
     h->host_pb.c.T = cfg->n_time;
@@ -217,6 +224,7 @@ void mems_destroy(mems_handle_t h) {
     cudaFree(h->chains.scale_cw); cudaFree(h->chains.lambda_cw); cudaFree(h->chains.win_cw);
     cudaFree(h->chains.llc); cudaFree(h->chains.prom_count); cudaFree(h->chains.rows_eval);
     cudaFree(h->dev_coarse);
+    cudaFree(h->dev_coarse_wimg);
     delete h->host_coarse;
     delete h;
 }
@@ -369,6 +377,13 @@ int mems_set_coarse_fft(mems_handle_t h, const float* const* W, const float* con
     }
     if (h->host_pb.c.T < 2 * MEMS_COARSE_HARM + 1)
         return fail(MEMS_E_INVALID, "the FFT coarse surrogate needs n_time >= %d", 2 * MEMS_COARSE_HARM + 1);
+    if (h->cfg.path == MEMS_PATH_TC) {                    // operand image for the tensor-core coarse pass
+        std::vector<unsigned char> img(mems_tc_coarse_wimg_bytes());
+        mems_tc_build_coarse_wimg(cm, P, img.data());
+        if (!h->dev_coarse_wimg) CUDA_TRY(cudaMalloc(&h->dev_coarse_wimg, img.size()));
+        CUDA_TRY(cudaMemcpy(h->dev_coarse_wimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+        cm.wimg = static_cast<const unsigned char*>(h->dev_coarse_wimg);
+    }
     h->have_coarse = true;
     h->have_chains = false;
     if (h->host_yobs.empty()) CUDA_TRY(cudaMemcpy(h->dev_coarse, h->host_coarse, sizeof(MemsCoarse), cudaMemcpyHostToDevice));
@@ -416,6 +431,10 @@ static int run_common(mems_handle_t h, MemsRunArgs& ra, void* stream) {
     ra.n_sub = (h->sampler == MEMS_MODE_CW) ? h->host_pb.c.P : (h->sampler == MEMS_MODE_DA ? 2 : 1);
     ra.da_stride = h->da_stride;
     ra.coarse = (h->sampler == MEMS_MODE_DA && h->use_coarse) ? h->dev_coarse : nullptr;
+    // the coarse stage runs on the tensor cores when its staging blocks fit next to the resident fine weights (MEMS_COARSE_FP32=1
+    // in the environment keeps it on the CUDA cores: A/B and fallback)
+    ra.coarse_tc = (ra.coarse && h->cfg.path == MEMS_PATH_TC && h->dev_coarse_wimg && mems_tc_coarse_fits(h->host_pb.c.T, h->smem_optin) &&
+                    !getenv("MEMS_COARSE_FP32")) ? 1 : 0;
     ra.target_acc = (h->sampler == MEMS_MODE_CW) ? 0.21 / h->host_pb.c.P + 0.23 : 0.234;
     MemsLaunchCtx ctx = make_ctx(h, stream);
     const int e = (h->cfg.path == MEMS_PATH_TC) ? mems_tc_run(ctx, ra) : mems_fp32_run(ctx, ra);

@@ -62,6 +62,10 @@ struct MemsCoarse {
     double mean[MEMS_PMAX], sscale[MEMS_PMAX];         // StandardScaler of the coarse model's inputs
     double sum_y2, sum_y;                              // sum y_obs^2, sum y_obs
     double cy[MEMS_COARSE_HARM], sy[MEMS_COARSE_HARM]; // sum_t y_obs[t] cos / sin(2 pi k t / T), k = 1..7
+    // tensor-core path: pre-swizzled fp16 operand blocks of the coarse model in global memory (streamed layer by layer into
+    // a shared-memory staging area, mems_tc.cu) and the hidden-layer biases times 2 log2(e), preloaded into the accumulator
+    const unsigned char* wimg;
+    __align__(16) float tcbias[MEMS_NLAYER_H * MEMS_WIDTH];   // float4 loads
 };
 
 // Mutable chain state, SoA over chains.
@@ -94,6 +98,7 @@ struct MemsRunArgs {
     int n_sub;                         // surrogate evaluations per update: 1 (RW), P (CW), 2 (DA)
     int da_stride;                     // DA: the coarse stage scores every da_stride-th time point
     const MemsCoarse* coarse;          // DA: non-null -> the coarse stage is the FFT surrogate instead (da_stride unused)
+    int coarse_tc;                     // tensor-core path: 1 -> the FFT surrogate runs on the tensor cores too (staging fits)
     double target_acc;                 // adaptation target: 0.234 (RW), 0.21/P + 0.23 (CW)
     unsigned long long step0;          // updates already done (global sample index of the state)
     const double* xi;                  // explicit mode: [n_steps][P][C] (RW/DA: chol*z; CW: z), else nullptr

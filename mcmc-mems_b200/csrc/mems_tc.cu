@@ -57,11 +57,75 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
 // surrogate pass the group announces (ctrl_tiles via bar_S) tiles slot, slot + GSLOT, ...; ctrl_tiles < 0 ends the loop.
 // Per tile: layer 0 waits for the tail warps' layer-1 operand, layers 1..5 for the hidden warps' A operands; every
 // accumulator goes to the hidden warps (bar_Dh).  g, slot0 must be warp-uniform.
+// Coarse pass (FFT surrogate of delayed acceptance), MMA side: one tile in slot 0, seven GEMM layers whose B operands are
+// streamed from the global image `cimg` into the staging blocks just before they are needed:
+//   layer 0          K = 32 over the split inputs (bias rides on the ones columns)            stage A <- layer-1 block
+//   layers 1..5      a_lo W_hi + a_hi W_lo + a_hi W_hi ON TOP of the bias the hidden warps     stage A <- W_hi, stage B <- W_lo
+//                    wrote into the accumulator (tcgen05.st) -- no bias MMA
+//   output layer     N = 16 (15 features), no bias (added in FP32 by the tail warps)           stage A <- hi | lo blocks
+// A staging block is overwritten only after the MMAs that read it have completed (the issuer waits for its own previous
+// commit on bar_Dh); the copy overlaps the hidden warps' epilogue.  ph bit 5: bar_W parity.
+__device__ __forceinline__ void issue_coarse_pass(GroupSmem& gs, uint32_t d, const unsigned char* cimg, uint32_t stageA,
+                                                  uint32_t& ph, uint32_t& nD, uint32_t aAt, uint32_t aAh, uint32_t aDh) {
+    const uint32_t stageB = smem_u32(&gs.cb.scale_cw[0][0]);
+    const uint32_t aW = smem_u32(&gs.bar_W);
+#pragma unroll 1
+    for (int layer = 0; layer <= MEMS_HIDDEN; ++layer) {
+        if (layer > 0) mbar_wait_a(aDh, (nD - 1u) & 1u);                 // the previous layer's MMAs are done with the staging blocks
+        if (elect_one()) {
+            if (layer == 0) {
+                mbar_arrive_expect_tx(&gs.bar_W, (uint32_t)BLK);
+                bulk_g2s_a(stageA, cimg + (size_t)CBLK_B1 * BLK, BLK, aW);
+            } else if (layer < MEMS_HIDDEN) {
+                mbar_arrive_expect_tx(&gs.bar_W, (uint32_t)(2 * BLK));
+                bulk_g2s_a(stageA, cimg + (size_t)(CBLK_WHI + layer - 1) * BLK, BLK, aW);
+                bulk_g2s_a(stageB, cimg + (size_t)(CBLK_WLO + layer - 1) * BLK, BLK, aW);
+            } else {
+                mbar_arrive_expect_tx(&gs.bar_W, 4096u);
+                bulk_g2s_a(stageA, cimg + (size_t)CBLK_WO * BLK, 4096u, aW);
+            }
+        }
+        __syncwarp();
+        if (layer == 0) { mbar_wait_a(aAt, (ph >> 2) & 1u); ph ^= 4u; }
+        else { mbar_wait_a(aAh, ph & 1u); ph ^= 1u; }
+        mbar_wait_a(aW, (ph >> 5) & 1u);
+        ph ^= 32u;
+        tc_fence_after();
+        if (elect_one()) {
+            const uint64_t bA = make_desc(stageA), bB = make_desc(stageB);
+            if (layer == 0) {
+                umma_ts(d, d + 64, bA, 0u);
+                umma_ts(d, d + 64 + 8, bA + 2, 1u);
+            } else if (layer < MEMS_HIDDEN) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, bA + 2 * ks, 1u);     // a_lo * W_hi (+ preloaded bias)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, bB + 2 * ks, 1u);     // a_hi * W_lo
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, bA + 2 * ks, 1u);     // a_hi * W_hi
+            } else {
+                const uint64_t bL = make_desc(stageA + 2048u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_n16(d, d + 96 + 8 * ks, bA + 2 * ks, ks > 0 ? 1u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_n16(d, d + 64 + 8 * ks, bL + 2 * ks, 1u);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma_ts_n16(d, d + 64 + 8 * ks, bA + 2 * ks, 1u);
+            }
+            umma_commit_a(aDh);
+        }
+        ++nD;
+        __syncwarp();
+    }
+}
+
 template <int NSLOT>
-__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g, int slot0) {
+__device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g, int slot0, const unsigned char* cimg = nullptr,
+                                                uint32_t stageA = 0u) {
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
-    uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S
+    uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S; bit 5: bar_W
+    uint32_t nD = 0;                  // commits issued on slot 0 so far (phase of bar_Dh[0] the next commit completes)
     const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
     const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
     const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
@@ -70,6 +134,10 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
         ph ^= 16u;
         const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
         if (n_tiles < 0) break;
+        if (n_tiles == COARSE_TILES) {                                   // only the issuer of slot 0 is woken for a coarse pass
+            issue_coarse_pass(gs, base, cimg, stageA, ph, nD, aAt, aAh, aDh);
+            continue;
+        }
         for (int t0 = 0; t0 < n_tiles; t0 += GSLOT) {
 #pragma unroll 1
             for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
@@ -89,6 +157,7 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                             issue_layer(wimg, base + s * 128, layer);
                             umma_commit_a(aDh + 8 * s);
                         }
+                        if (s == 0) ++nD;
                         __syncwarp();
                     }
                 }
@@ -101,9 +170,10 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
 __device__ __forceinline__ void announce_tiles(GroupSmem& gs, int n_tiles) {
     *reinterpret_cast<volatile int*>(&gs.ctrl_tiles) = n_tiles;
     if (MEMS_ISSUER_PER_SLOT) {
+        const int n_slots = (n_tiles == COARSE_TILES) ? 1 : n_tiles;       // a coarse pass is one tile in slot 0
 #pragma unroll
         for (int s = 0; s < GSLOT; ++s)
-            if (n_tiles < 0 || s < n_tiles) mbar_arrive(&gs.bar_S[s]);     // an issuer without a tile in this pass is not woken
+            if (n_tiles < 0 || s < n_slots) mbar_arrive(&gs.bar_S[s]);     // an issuer without a tile in this pass is not woken
     } else {
         mbar_arrive(&gs.bar_S[0]);
     }
@@ -316,6 +386,116 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     group_bar_sync(g);                                 // Sfin[chain] may have been written by another thread
 }
 
+// K-slot layout of a layer-1 operand with NIN inputs (coarse model: the P parameters, no time column)
+template <int NIN>
+__device__ __forceinline__ void put_input_n(uint32_t (&a1)[16], int i, float v) {
+    float h, m, l;
+    split3(v, h, m, l);
+    set_half<0>(a1, 0 * NIN + i, h);
+    set_half<0>(a1, 1 * NIN + i, m);
+    set_half<0>(a1, 2 * NIN + i, l);
+    set_half<0>(a1, 3 * NIN + i, h);
+    set_half<0>(a1, 4 * NIN + i, m);
+}
+
+// Coarse pass (FFT surrogate, delayed-acceptance first stage) on the tensor cores, epilogue side: the gs.nlive proposals
+// listed in gs.map are the rows of ONE tile in slot 0 (row i = live chain i); result gs.Sfin[chain] = ||y_obs - y_c||^2.
+//   tail warps     scaled inputs (f64 scale, f32 cast: utils.py:38-39 convention) -> three-way split layer-1 operand;
+//                  after the output layer: 15 features + bias -> band-limited misfit (same arithmetic as coarse_fft_pass)
+//   hidden warps   six tanh epilogues (identical to the fine model's) and, for layers 1..5, the NEXT layer's bias
+//                  written into the accumulator columns they have just read (the MMAs of that layer accumulate onto it)
+template <int P>
+__device__ __forceinline__ void tc_coarse_group(TcSmem& sm, GroupSmem& gs, int g, int gt, const MemsCoarse* __restrict__ cm,
+                                                int T, uint32_t& ph) {
+    const bool is_tail = gt >= HTHREADS;
+    const int row = is_tail ? gt - HTHREADS : (gt & 127);
+    const int q = row >> 5;
+    const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);     // slot 0 of the group
+    if (gt == 0) announce_tiles(gs, COARSE_TILES);
+    if (!is_tail) {
+        constexpr int NCOL = 64 / NH;
+        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
+        const int h = gt >> 7;
+        const uint32_t aDh = smem_u32(&gs.bar_Dh[0]), aAh = smem_u32(&gs.bar_Ah[0]), aX = smem_u32(&gs.bar_X[0]);
+#pragma unroll 1
+        for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+            mbar_wait_a(aDh, ph & 1u);
+            ph ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int pc = 0; pc < NCOL / EC; ++pc) {
+                uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
+                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
+                tc_wait_ld();
+                epilogue_split_v2<EC / 8, false, 0>(w, hi2, lo2);
+                tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
+                tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
+            }
+            if (layer < MEMS_NLAYER_H) {                   // bias of hidden layer `layer` (the next GEMM) into D
+                const float4* b4 = reinterpret_cast<const float4*>(cm->tcbias + layer * MEMS_WIDTH + NCOL * h);
+#pragma unroll
+                for (int c8 = 0; c8 < NCOL / 8; ++c8) {
+                    const float4 u = __ldg(b4 + 2 * c8), v = __ldg(b4 + 2 * c8 + 1);
+                    const uint32_t bw[8] = {__float_as_uint(u.x), __float_as_uint(u.y), __float_as_uint(u.z), __float_as_uint(u.w),
+                                            __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+                    tmem_st8(tD + NCOL * h + 8 * c8, bw);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive_a(aAh);
+        }
+        mbar_wait_a(aDh, ph & 1u);                         // output layer complete: relay to the tail warps
+        ph ^= 1u;
+        tc_fence_after();
+        tc_fence_before();
+        mbar_arrive_a(aX);
+    } else {
+        const bool live = row < gs.nlive;
+        const int j = live ? (int)gs.map[row] : 0;
+        uint32_t a1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a1[i] = 0u;
+        if (live) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+                put_input_n<P>(a1, p, (float)((gs.cb.xp[p][j] - cm->mean[p]) / cm->sscale[p]));
+        }
+        set_half<0>(a1, 5 * P + 0, 1.0f);                   // ones that pick up b_hi, b_mid, b_lo
+        set_half<0>(a1, 5 * P + 1, 1.0f);
+        set_half<0>(a1, 5 * P + 2, 1.0f);
+        tmem_st16(tD + 64, a1);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&gs.bar_At[0]);
+        mbar_wait(&gs.bar_X[0], ph & 1u);
+        ph ^= 1u;
+        tc_fence_after();
+        uint32_t fw[16];
+        tmem_ld16(tD, fw);
+        tc_wait_ld();
+        tc_fence_before();                                  // the accumulator has been read: slot 0 may be restaged
+        if (live) {
+            float f[16];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) f[o] = __uint_as_float(fw[o]) + __ldg(&cm->bo[o]);
+            const double m = 0.1 * (double)f[0];
+            double dot = m * cm->sum_y, nrm = (double)T * m * m;
+            const double w2 = 2.0 / (double)T;
+#pragma unroll 1
+            for (int k = 0; k < MEMS_COARSE_HARM; ++k) {
+                const double A = (double)f[1 + k], phi = 0.01 * (double)f[1 + MEMS_COARSE_HARM + k];
+                double sn, cs;
+                sincos(phi, &sn, &cs);
+                dot += w2 * A * (cs * cm->cy[k] - sn * cm->sy[k]);
+                nrm += w2 * A * A;
+            }
+            gs.Sfin[j] = cm->sum_y2 - 2.0 * dot + nrm;
+        }
+    }
+    group_bar_sync(g);                                      // Sfin[] is complete
+}
+
 // Compaction of the chains that need the coming pass: gs.map / gs.nlive (first warp of the group; ballot prefix sums).
 __device__ __forceinline__ void group_compact_live(GroupSmem& gs, int g, int gt, int ncv) {
     group_bar_sync(g);                                 // live[] of every chain is written
@@ -363,6 +543,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
                 mbar_init(&sm.grp[g].bar_X[s], HTHREADS);
             }
             for (int s = 0; s < GSLOT; ++s) mbar_init(&sm.grp[g].bar_S[s], 1);
+            mbar_init(&sm.grp[g].bar_W, 1);
             sm.grp[g].ctrl_tiles = 0;
         }
         mbar_init(&sm.bar_w, 1);
@@ -417,7 +598,10 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     if (gt < 0) {
         const int gw = __shfl_sync(0xffffffffu, g, 0);                   // provably warp-uniform group index
         const int sw = __shfl_sync(0xffffffffu, -1 - gt, 0);             // and first slot
-        mma_issuer_loop<MEMS_ISSUER_PER_SLOT ? 1 : GSLOT>(sm, sm.grp[gw], gw, sw);
+        // coarse pass on the tensor cores: stage A of the group = extra dynamic shared memory behind the time column
+        const uint32_t stage0 = (smem_u32(s_ts + T) + 1023u) & ~1023u;
+        const unsigned char* cimg = ra.coarse_tc ? ra.coarse->wimg : nullptr;
+        mma_issuer_loop<MEMS_ISSUER_PER_SLOT ? 1 : GSLOT>(sm, sm.grp[gw], gw, sw, cimg, stage0 + (uint32_t)(gw * BLK));
     } else {
         uint32_t ph = 0;
         for (int batch = gid; batch < nbatch; batch += gstride) {
@@ -432,7 +616,9 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                     // proposals the DA first stage did not promote drop out); no live chain -> the pass is skipped
                     group_compact_live(gs, g, gt, ncv);
                     const bool any = gs.nlive > 0;
-                    if (any && batch_pass_is_coarse_model(ra, sub))   // DA first stage on the FFT surrogate (FP32, CUDA cores)
+                    if (any && batch_pass_is_coarse_model(ra, sub) && ra.coarse_tc)   // DA first stage on the FFT surrogate
+                        tc_coarse_group<P>(sm, gs, g, gt, ra.coarse, T, ph);
+                    else if (any && batch_pass_is_coarse_model(ra, sub))   // ... on CUDA cores when the staging blocks do not fit
                         coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, coarse_scratch(gs.cb), gt,
                                         GTHREADS, [g] { group_bar_sync(g); });
                     else if (any) {
@@ -546,6 +732,51 @@ int launch_by_p(int Pv, K1 k1, K2 k2, K3 k3, K4 k4, int grid, size_t smem, cudaS
 
 size_t mems_tc_wimg_bytes() { return WIMG_BYTES; }
 
+// ---- coarse (FFT) surrogate on the tensor cores: global-memory operand image, streamed by the MMA issuer -------------
+size_t mems_tc_coarse_wimg_bytes() { return COARSE_WIMG_BYTES; }
+
+// Does the extra staging block of every group fit behind the observation / time columns?
+bool mems_tc_coarse_fits(int T, size_t smem_optin) { return tc_smem_bytes(T) + COARSE_STAGE_BYTES <= smem_optin; }
+
+// cm: the FP32 coarse model (Keras layout).  host_img: COARSE_WIMG_BYTES.  Also fills cm.tcbias (2 log2(e) * bh).
+void mems_tc_build_coarse_wimg(MemsCoarse& cm, int P, void* host_img) {
+    unsigned char* img = static_cast<unsigned char*>(host_img);
+    memset(img, 0, COARSE_WIMG_BYTES);
+    for (int n = 0; n < MEMS_WIDTH; ++n) {              // layer 1: K slots term * P + i, terms 0..2 carry W_hi, 3..4 W_lo
+        for (int i = 0; i < P; ++i) {
+            const double w = C2 * (double)cm.W1[i * MEMS_WIDTH + n];
+            const double whi = h_val(w), wlo = h_val(w - whi);
+            put(img, CBLK_B1, n, 0 * P + i, whi);
+            put(img, CBLK_B1, n, 1 * P + i, whi);
+            put(img, CBLK_B1, n, 2 * P + i, whi);
+            put(img, CBLK_B1, n, 3 * P + i, wlo);
+            put(img, CBLK_B1, n, 4 * P + i, wlo);
+        }
+        const double b = C2 * (double)cm.b1[n];
+        const double bh = h_val(b), bm = h_val(b - bh), bl = h_val(b - bh - bm);
+        put(img, CBLK_B1, n, 5 * P + 0, bh);
+        put(img, CBLK_B1, n, 5 * P + 1, bm);
+        put(img, CBLK_B1, n, 5 * P + 2, bl);
+    }
+    for (int h = 0; h < MEMS_NLAYER_H; ++h)
+        for (int n = 0; n < MEMS_WIDTH; ++n) {
+            for (int k = 0; k < MEMS_WIDTH; ++k) {
+                const double w = C2 * (double)cm.Wh[(h * MEMS_WIDTH + k) * MEMS_WIDTH + n];
+                const double whi = h_val(w);
+                put(img, CBLK_WHI + h, n, k, whi);
+                put(img, CBLK_WLO + h, n, k, w - whi);
+            }
+            cm.tcbias[h * MEMS_WIDTH + n] = (float)(C2 * (double)cm.bh[h * MEMS_WIDTH + n]);
+        }
+    for (int o = 0; o < 16; ++o)                          // output layer, linear: B[o][k] = Wo[k][o]; lo block 2 KB further
+        for (int k = 0; k < MEMS_WIDTH; ++k) {
+            const double w = (o < MEMS_COARSE_OUT) ? (double)cm.Wo[k * 16 + o] : 0.0;
+            const double whi = h_val(w);
+            put(img, CBLK_WO, o, k, whi);
+            put(img + 2048, CBLK_WO, o, k, w - whi);
+        }
+}
+
 // largest trace length whose observation / time columns fit next to the resident weights in `smem_optin` bytes
 int mems_tc_max_time_points(size_t smem_optin) {
     const size_t fixed = tc_smem_bytes(0);
@@ -619,7 +850,7 @@ void mems_tc_build_wimg(const MemsProblem& pb, void* host_img) {
 }
 
 int mems_tc_run(const MemsLaunchCtx& ctx, const MemsRunArgs& ra) {
-    const size_t smem = tc_smem_bytes(ctx.pb_host->c.T);
+    const size_t smem = tc_smem_bytes(ctx.pb_host->c.T) + (ra.coarse_tc ? COARSE_STAGE_BYTES : 0);
     const int nbatch = (ctx.chains.C + ra.nc - 1) / ra.nc;
     const int want = (nbatch + NGROUP - 1) / NGROUP;
     const int grid = want < ctx.sm_count ? want : ctx.sm_count;

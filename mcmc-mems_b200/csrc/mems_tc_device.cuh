@@ -78,9 +78,25 @@ constexpr double C2 = 2.0 * 1.4426950408889634074;     // 2*log2(e)
 
 // instruction descriptor, kind::f16: D=f32, A=B=f16, K-major both, N=64, M=128
 constexpr uint32_t IDESC = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC_N16 = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);   // the coarse model's 64 -> 15 (padded 16) layer
 
-struct GroupSmem {
-    ChainBatch cb;
+// Coarse (FFT) surrogate of delayed acceptance on the tensor cores: its operand blocks stay in global memory (L2) and are
+// streamed one layer at a time into two 8 KB staging blocks per group: `stage A` (extra dynamic shared memory behind the
+// observation / time columns) takes the layer-1 block, W_hi of a hidden layer or the output layer's hi / lo blocks,
+// `stage B` (the batch's component-wise scale arrays, which delayed acceptance never uses) takes W_lo.
+constexpr int CBLK_B1 = 0;            // layer-1 B operand (P inputs, no time column)
+constexpr int CBLK_WHI = 1;           // 5 blocks
+constexpr int CBLK_WLO = 6;           // 5 blocks
+constexpr int CBLK_WO = 11;           // output layer [16 rows][64 k]: hi block at +0, lo block at +2048 (2 KB each)
+constexpr int CNBLK = 12;
+constexpr int COARSE_WIMG_BYTES = CNBLK * BLK;
+constexpr int COARSE_TILES = 0x40000000;   // ctrl_tiles value that announces a coarse pass (one tile, slot 0)
+constexpr int COARSE_STAGE_BYTES = NGROUP * BLK + 1024;   // extra dynamic shared memory (stage A of both groups + alignment slack)
+static_assert(offsetof(ChainBatch, scale_cw) % 1024 == 0, "stage B must be 1024-byte aligned inside the batch");
+static_assert(sizeof(double) * 2 * MEMS_PMAX * MEMS_NCMAX >= BLK, "stage B does not fit in scale_cw + lambda_cw");
+
+struct alignas(1024) GroupSmem {
+    ChainBatch cb;                     // 1024-aligned: cb.scale_cw doubles as a swizzled operand block in the coarse pass
     double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (tail threads)
     double R2[GSLOT][128];             // dense passes: squared residual of every row of the slot's tile
     unsigned long long bar_At[GSLOT];  // tail -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
@@ -90,7 +106,8 @@ struct GroupSmem {
     float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves
     unsigned long long bar_S[GSLOT];   // group -> MMA issuer of the slot: ctrl_tiles of the next pass is valid (signalled only when
                                        // the pass has a tile for that slot, or to end: every signalled phase is consumed before the next)
-    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work
+    unsigned long long bar_W;          // bulk copy -> MMA issuer: the coarse model's operand blocks of a layer are staged
+    int ctrl_tiles;                    // tiles of the coming pass, -1 = no more work, COARSE_TILES = coarse pass
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
@@ -212,6 +229,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // one lane of a converged warp (CUTLASS idiom): the warp stays convergent around the elected instruction, so
 // warp-uniform operands remain in uniform registers (no per-lane "waterfall" loop around UTCHMMA)
 __device__ __forceinline__ bool elect_one() {
@@ -235,6 +257,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return d;
 }
 
+__device__ __forceinline__ void umma_ts_n16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(IDESC_N16), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"

@@ -677,12 +677,17 @@ def test_sensitivity_push_forward_matches_oracle():
     assert batched["values"].shape == (2000,) and batched["mean"] == pytest.approx(out["mean"], rel=1e-6)
 
 
-@pytest.mark.parametrize("path", PATHS, ids=PATH_IDS)
+@pytest.mark.parametrize("path", [0, 1, 2], ids=["fp32", "tc", "tc_coarse_on_cuda_cores"])
 @pytest.mark.parametrize("cpb", [0, 44], ids=["auto", "one_batch"])
-def test_delayed_acceptance_with_fft_coarse_surrogate(path, cpb):
+def test_delayed_acceptance_with_fft_coarse_surrogate(path, cpb, monkeypatch):
     """DA whose first stage is the reference's FFT surrogate + reconstruction (oracle/coarse.py): start-state coarse
-    log-likelihoods and every two-stage decision replayed by the oracle (Q-factor problem, P = 4)."""
+    log-likelihoods and every two-stage decision replayed by the oracle (Q-factor problem, P = 4).  On the tensor-core path
+    the coarse model runs through the tcgen05 pipeline too (operand blocks streamed from L2 layer by layer); the third
+    variant keeps it on the CUDA cores inside the same kernel (the fallback when the staging blocks do not fit)."""
     from mcmc_mems_b200 import engine as E
+    if path == 2:
+        monkeypatch.setenv("MEMS_COARSE_FP32", "1")
+        path = 1
     pb = helpers.load_problem("qfactor")
     cf = helpers.fft_coarse()
     coarse = helpers.coarse_ll_fn(pb, cf)

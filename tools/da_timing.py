@@ -42,7 +42,11 @@ for name, sampler, kw, scale0 in (("mh", E.SAMPLER_MH, {}, 0.128), ("da stride 4
 pbq = helpers.load_problem("qfactor")
 cf = helpers.fft_coarse()
 x0q = np.tile(pbq["x_opts"], (C // 5 + 1, 1))[:C]
-for name, setup in (("qf mh", None), ("qf da stride 4", "stride"), ("qf da fft", "fft")):
+for name, setup in (("qf mh", None), ("qf da stride 4", "stride"), ("qf da fft", "fft"), ("qf da fft, coarse on CUDA cores", "fft_fp32")):
+    os.environ.pop("MEMS_COARSE_FP32", None)
+    if setup == "fft_fp32":                       # the same kernel with the coarse stage on the CUDA cores (round-1 arrangement)
+        os.environ["MEMS_COARSE_FP32"] = "1"
+        setup = "fft"
     eng = helpers.engine(pbq, C, 1)
     if setup == "stride":
         eng.set_sampler(E.SAMPLER_DA, da_stride=4)
@@ -58,5 +62,5 @@ for name, setup in (("qf mh", None), ("qf da stride 4", "stride"), ("qf da fft",
     dt = time.perf_counter() - t0
     acc = eng.state()["accept_count"].double().mean().item() / (steps + 20)
     extra = f", promoted {eng.aux_state()['promote_count'].double().mean().item() / (steps + 20):.3f}" if setup else ""
-    print(f"{name:14s} {C} chains: {C * steps / dt / 1e6:8.2f} M chain-steps/s, acceptance {acc:.3f}{extra}")
+    print(f"{name:32s} {C} chains: {C * steps / dt / 1e6:8.2f} M chain-steps/s, acceptance {acc:.3f}{extra}")
     eng.close()
