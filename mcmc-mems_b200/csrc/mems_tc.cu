@@ -41,14 +41,16 @@ __device__ __forceinline__ void issue_layer(uint32_t wimg_saddr, uint32_t d, int
         const uint64_t whi = make_desc(wimg_saddr + (BLK_WHI + h) * BLK);
         const uint64_t wlo = make_desc(wimg_saddr + (BLK_WLO + h) * BLK);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, whi + 2 * ks, ks > 0 ? 1u : 0u);   // a_lo * W_hi
+        for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, whi + 2 * ks, (ks > 0 || MEMS_BIAS_PRELOAD) ? 1u : 0u);   // a_lo * W_hi
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, wlo + 2 * ks, 1u);                 // a_hi * W_lo
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, whi + 2 * ks, 1u);                 // a_hi * W_hi
-        const uint64_t ones = make_desc(wimg_saddr + BLK_ONES * BLK);
-        const uint64_t bias = make_desc(wimg_saddr + (BLK_BIAS + (h >> 2)) * BLK) + 2 * (h & 3);
-        umma_ss(d, ones, bias, 1u);                                                                    // + bias
+        if (!MEMS_BIAS_PRELOAD) {
+            const uint64_t ones = make_desc(wimg_saddr + BLK_ONES * BLK);
+            const uint64_t bias = make_desc(wimg_saddr + (BLK_BIAS + (h >> 2)) * BLK) + 2 * (h & 3);
+            umma_ss(d, ones, bias, 1u);                                                                // + bias
+        }
     }
 }
 
@@ -261,6 +263,20 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                                 epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
                                 tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
                                 tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
+                            }
+                            if (MEMS_BIAS_PRELOAD) {           // bias of the next GEMM into the accumulator columns just read
+                                const float4* b4 = reinterpret_cast<const float4*>(sm.tcbias + layer * MEMS_WIDTH + NCOL * h);
+#pragma unroll
+                                for (int c16 = 0; c16 < NCOL / 16; ++c16) {
+                                    uint32_t bw[16];
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) {
+                                        const float4 u = b4[4 * c16 + v];
+                                        bw[4 * v] = __float_as_uint(u.x); bw[4 * v + 1] = __float_as_uint(u.y);
+                                        bw[4 * v + 2] = __float_as_uint(u.z); bw[4 * v + 3] = __float_as_uint(u.w);
+                                    }
+                                    tmem_st_n<16>(tD + NCOL * h + 16 * c16, bw);
+                                }
                             }
                             tc_wait_st();
                             tc_fence_before();
@@ -563,6 +579,8 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
         }
     }
     for (int i = tid; i < pb.c.T; i += NTHREADS) { s_yobs[i] = pb.yobs[i]; s_ts[i] = pb.ts[i]; }
+    if (MEMS_BIAS_PRELOAD)
+        for (int i = tid; i < MEMS_NLAYER_H * MEMS_WIDTH; i += NTHREADS) sm.tcbias[i] = (float)(C2 * (double)pb.bh[i]);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

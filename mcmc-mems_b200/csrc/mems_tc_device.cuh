@@ -18,6 +18,10 @@
 #ifndef MEMS_TAIL_WAIT_HINT_NS
 #define MEMS_TAIL_WAIT_HINT_NS 0   // > 0: suspend-time hint of the tail warps' wait for a tile's output dots
 #endif
+#ifndef MEMS_BIAS_PRELOAD
+#define MEMS_BIAS_PRELOAD 0    // 1: the hidden warps write the next layer's bias into the accumulator (tcgen05.st) instead of the
+#endif                         //    shared-memory-operand bias MMA (13 -> 12 MMAs per layer).  Measured: 40.1 vs 41.4 M chain-steps/s --
+                               //    the 12 extra epilogue instructions per thread cost more than the 75 tensor cycles save
 #ifndef MEMS_EX2_MIX
 #define MEMS_EX2_MIX 0         // (round-1 arithmetic, micro-benchmarks only) share of exponentials on the FMA pipe
 #endif
@@ -126,6 +130,7 @@ struct TcSmem {
     float w7[64];
     float b7;
     float pad_[3];
+    __align__(16) float tcbias[MEMS_NLAYER_H * MEMS_WIDTH];   // 2 log2(e) * hidden-layer biases (MEMS_BIAS_PRELOAD)
     MemsConsts c;
     GroupSmem grp[NGROUP];
     unsigned long long bar_w;
