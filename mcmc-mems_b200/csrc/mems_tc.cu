@@ -219,6 +219,39 @@ __device__ __forceinline__ void group_bar_sync(int g) { named_bar_sync(1 + g, GT
 // = (time f / n_live, chain slot f mod n_live), so every tile is full even when n_live does not divide 128.  A tail
 // thread then meets a different chain in every tile: the squared residuals of a tile go through shared memory (gs.R2)
 // and tail thread c < n_live adds the entries of chain slot c in time order (deterministic).
+// One thread's share of a tile-layer epilogue: NCH pieces of eight accumulator columns from column c0 of the slot at tD.
+// Piece by piece (a finer grain than the whole row keeps XU, FMA and ALU work of one warp interleaved,
+// profiles/r02_microbench_*): tcgen05.ld -> tanh -> fp16 hi/lo split -> tcgen05.st of the next layer's A operand words.
+template <int NCH>
+__device__ __forceinline__ void epi_split_chunks(uint32_t tD, int c0) {
+#pragma unroll
+    for (int pc = 0; pc < NCH; ++pc) {
+        uint32_t w[8], hi2[4], lo2[4];
+        tmem_ld8(tD + c0 + 8 * pc, w);
+        tc_wait_ld();
+        epilogue_split_v2<1, false, 0>(w, hi2, lo2);
+        tmem_st4(tD + 64 + (c0 >> 1) + 4 * pc, hi2);
+        tmem_st4(tD + 96 + (c0 >> 1) + 4 * pc, lo2);
+    }
+}
+
+// The same for the last tanh layer: its activations go straight into the 64 -> 1 output layer (partial dot over the
+// thread's columns; w7p: output weights permuted per group of eight, see epilogue_dot8).
+template <int NCH>
+__device__ __forceinline__ float epi_dot_chunks(uint32_t tD, int c0, const float* w7p) {
+    uint64_t acc = pk(0.0f, 0.0f);
+#pragma unroll
+    for (int pc = 0; pc < NCH; ++pc) {
+        uint32_t w[8];
+        tmem_ld8(tD + c0 + 8 * pc, w);
+        tc_wait_ld();
+        acc = epilogue_dot8(w, w7p + c0 + 8 * pc, acc);
+    }
+    float oa, ob;
+    upk(acc, oa, ob);
+    return oa + ob;
+}
+
 template <int P, bool DENSE>
 __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, int gt, const double* s_yobs,
                                               const float* s_ts, int T, int stride, int nc, int ncv,
@@ -235,9 +268,8 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     if (gt == 0) announce_tiles(gs, n_tiles);
 
     if (!is_tail) {
-        // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand, layers 0..4 of every tile
-        constexpr int NCOL = 64 / NH;                 // accumulator columns per thread
-        const int h = gt >> 7;                        // column half
+        // ---- hidden-layer warps: accumulator -> tanh -> fp16 hi/lo split -> next A operand; last layer -> partial output dot
+        const int cb0 = HCOLS * (gt >> 7);            // first accumulator column of this thread
         const uint32_t aDh = keep_in_register(smem_u32(&gs.bar_Dh[0]));
         const uint32_t aAh = aDh - (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_Ah));
         const uint32_t aX = aDh + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_Dh));
@@ -251,50 +283,23 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                         mbar_wait_a(aDh + 8 * s, (ph >> s) & 1u);
                         ph ^= (1u << s);
                         tc_fence_after();
-                        // the thread's NCOL accumulator columns in pieces of EC: load, tanh, hi/lo split, store (a finer grain
-                        // than the whole row keeps XU, FMA and ALU work of one warp interleaved: profiles/r02_microbench_*)
-                        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
                         if (layer < MEMS_HIDDEN - 1) {
-#pragma unroll
-                            for (int pc = 0; pc < NCOL / EC; ++pc) {
-                                uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
-                                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                                tc_wait_ld();
-                                epilogue_split_v2<EC / 8, (MEMS_EPI_R16 != 0) && (EC >= 16), MEMS_EPI_POLY8>(w, hi2, lo2);
-                                tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
-                                tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
-                            }
+                            epi_split_chunks<HCOLS / 8>(tD, cb0);
                             if (MEMS_BIAS_PRELOAD) {           // bias of the next GEMM into the accumulator columns just read
-                                const float4* b4 = reinterpret_cast<const float4*>(sm.tcbias + layer * MEMS_WIDTH + NCOL * h);
 #pragma unroll
-                                for (int c16 = 0; c16 < NCOL / 16; ++c16) {
-                                    uint32_t bw[16];
-#pragma unroll
-                                    for (int v = 0; v < 4; ++v) {
-                                        const float4 u = b4[4 * c16 + v];
-                                        bw[4 * v] = __float_as_uint(u.x); bw[4 * v + 1] = __float_as_uint(u.y);
-                                        bw[4 * v + 2] = __float_as_uint(u.z); bw[4 * v + 3] = __float_as_uint(u.w);
-                                    }
-                                    tmem_st_n<16>(tD + NCOL * h + 16 * c16, bw);
+                                for (int c8 = 0; c8 < HCOLS / 8; ++c8) {
+                                    const float4* b4 = reinterpret_cast<const float4*>(sm.tcbias + layer * MEMS_WIDTH + cb0 + 8 * c8);
+                                    const float4 u = b4[0], v = b4[1];
+                                    const uint32_t bw[8] = {__float_as_uint(u.x), __float_as_uint(u.y), __float_as_uint(u.z), __float_as_uint(u.w),
+                                                            __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+                                    tmem_st8(tD + cb0 + 8 * c8, bw);
                                 }
                             }
                             tc_wait_st();
                             tc_fence_before();
                             mbar_arrive_a(aAh + 8 * s);
                         } else {                               // last tanh layer . output weights: partial dot to the tail warps
-                            uint64_t acc = pk(0.0f, 0.0f);
-#pragma unroll
-                            for (int pc = 0; pc < NCOL / EC; ++pc) {
-                                uint32_t w[EC];
-                                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                                tc_wait_ld();
-#pragma unroll
-                                for (int g8 = 0; g8 < EC / 8; ++g8)
-                                    acc = epilogue_dot8(w + 8 * g8, sm.w7 + NCOL * h + EC * pc + 8 * g8, acc);
-                            }
-                            float oa, ob;
-                            upk(acc, oa, ob);
-                            gs.xchg[s][h][row] = oa + ob;
+                            gs.xchg[s][gt >> 7][row] = epi_dot_chunks<HCOLS / 8>(tD, cb0, sm.w7);
                             tc_fence_before();                 // the accumulator has been read: the slot may be restaged
                             mbar_arrive_a(aX + 8 * s);         // release: the store above is visible to the tail warps
                         }
@@ -303,13 +308,15 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             }
         }
     } else {
-        // ---- tail warps: layer-1 operands, last tanh layer + output layer, residuals
+        // ---- tail warps: layer-1 operands, residuals -- and (MEMS_TAIL_SHARE) the last TCOLS columns of every tile-layer
         const int jc = row % nce;                     // rows >= nce*tpt of a tile idle
         const int sub = row / nce;
         const int j = compact ? (int)gs.map[jc] : jc; // batch-local chain index
         const bool chain_live = (sub < tpt) && (compact || jc < ncv);
         const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
         const uint32_t aX = aAt + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_At));
+        const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
+        const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
         uint32_t a1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
@@ -339,49 +346,77 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             tc_fence_before();
             mbar_arrive_a(aAt + 8 * s);
         };
+        double Sp = 0.0;
+        // a tile's output is complete (own columns in `own`, the hidden warps' partial dots in xchg): residual, then the
+        // layer-1 operand of the slot's next tile
+        auto finish_tile = [&](int s, int tile, float own) {
+            mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
+            ph ^= (1u << s);
+            tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
+            const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + own + sm.b7;
+            if (DENSE) {
+                const int f = tile * 128 + row;
+                const int ti = f / nce;
+                double r2 = 0.0;
+                if (ti < Tn) {
+                    const double r = s_yobs[ti * stride] - (double)o;
+                    r2 = r * r;
+                }
+                gs.R2[s][row] = r2;
+                named_bar_sync(3 + g, TTHREADS);               // the tile's 128 residuals are in shared memory
+                if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
+                    int r0 = row - (tile * 128) % nce;
+                    if (r0 < 0) r0 += nce;
+                    for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
+                }
+                // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
+            } else {
+                const int ti = tile * tpt + sub;
+                const int t = ti * stride;
+                if (chain_live && ti < Tn) {
+                    if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
+                    const double r = s_yobs[t] - (double)o;
+                    Sp = fma(r, r, Sp);
+                }
+            }
+            // this slot's D and A are free again: stage the layer-1 operand of its next tile
+            const int nt = tile + GSLOT;
+            if (nt < n_tiles) stage_tile(s, nt);
+        };
 #pragma unroll
         for (int s = 0; s < GSLOT; ++s)
             if (s < n_tiles) stage_tile(s, s);
 
-        double Sp = 0.0;
         for (int pair = 0; pair < n_pairs; ++pair) {
+            if (MEMS_TAIL_SHARE) {
 #pragma unroll 1
-            for (int s = 0; s < GSLOT; ++s) {
-                const int tile = pair * 2 + s;
-                if (tile < n_tiles) {
-                    if (MEMS_TAIL_WAIT_HINT_NS > 0) mbar_wait_hint_a(aX + 8 * s, (ph >> s) & 1u, MEMS_TAIL_WAIT_HINT_NS);
-                    else mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
-                    ph ^= (1u << s);
-                    tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
-                    const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + sm.b7;
-                    if (DENSE) {
-                        const int f = tile * 128 + row;
-                        const int ti = f / nce;
-                        double r2 = 0.0;
-                        if (ti < Tn) {
-                            const double r = s_yobs[ti * stride] - (double)o;
-                            r2 = r * r;
-                        }
-                        gs.R2[s][row] = r2;
-                        named_bar_sync(3 + g, TTHREADS);               // the tile's 128 residuals are in shared memory
-                        if (row < nce) {                               // chain slot `row`: its rows of this tile, in time order
-                            int r0 = row - (tile * 128) % nce;
-                            if (r0 < 0) r0 += nce;
-                            for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
-                        }
-                        // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
-                    } else {
-                        const int ti = tile * tpt + sub;
-                        const int t = ti * stride;
-                        if (chain_live && ti < Tn) {
-                            if (y_out) y_out[(size_t)(c0 + j) * T + t] = o;
-                            const double r = s_yobs[t] - (double)o;
-                            Sp = fma(r, r, Sp);
+                for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
+#pragma unroll
+                    for (int s = 0; s < GSLOT; ++s) {
+                        const int tile = pair * 2 + s;
+                        if (tile < n_tiles) {
+                            const uint32_t tD = tD0 + s * 128;
+                            mbar_wait_a(aDh + 8 * s, (ph >> (2 + s)) & 1u);
+                            ph ^= (4u << s);
+                            tc_fence_after();
+                            if (layer < MEMS_HIDDEN - 1) {
+                                epi_split_chunks<TCOLS / 8>(tD, 2 * HCOLS);
+                                tc_wait_st();
+                                tc_fence_before();
+                                mbar_arrive_a(aAh + 8 * s);
+                            } else {
+                                const float own = epi_dot_chunks<TCOLS / 8>(tD, 2 * HCOLS, sm.w7);
+                                tc_fence_before();
+                                finish_tile(s, tile, own);
+                            }
                         }
                     }
-                    // this slot's D and A are free again: stage the layer-1 operand of its next tile
-                    const int nt = tile + GSLOT;
-                    if (nt < n_tiles) stage_tile(s, nt);
+                }
+            } else {
+#pragma unroll 1
+                for (int s = 0; s < GSLOT; ++s) {
+                    const int tile = pair * 2 + s;
+                    if (tile < n_tiles) finish_tile(s, tile, 0.0f);
                 }
             }
         }
@@ -428,39 +463,36 @@ __device__ __forceinline__ void tc_coarse_group(TcSmem& sm, GroupSmem& gs, int g
     const int q = row >> 5;
     const uint32_t tD = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);     // slot 0 of the group
     if (gt == 0) announce_tiles(gs, COARSE_TILES);
-    if (!is_tail) {
-        constexpr int NCOL = 64 / NH;
-        constexpr int EC = (MEMS_EPI_COLS < NCOL) ? MEMS_EPI_COLS : NCOL;
-        const int h = gt >> 7;
-        const uint32_t aDh = smem_u32(&gs.bar_Dh[0]), aAh = smem_u32(&gs.bar_Ah[0]), aX = smem_u32(&gs.bar_X[0]);
+    // this thread's accumulator columns: hidden threads HCOLS from HCOLS * half, tail threads (MEMS_TAIL_SHARE) the last TCOLS
+    const int cb0 = is_tail ? 2 * HCOLS : HCOLS * (gt >> 7);
+    const int nch = is_tail ? TCOLS / 8 : HCOLS / 8;
+    const uint32_t aDh = smem_u32(&gs.bar_Dh[0]), aAh = smem_u32(&gs.bar_Ah[0]), aX = smem_u32(&gs.bar_X[0]);
+    // six tanh epilogues; hidden threads wait on ph bit 0, tail threads (when they share the columns) on bit 2
+    auto tanh_layers = [&](uint32_t bit) {
 #pragma unroll 1
         for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
-            mbar_wait_a(aDh, ph & 1u);
-            ph ^= 1u;
+            mbar_wait_a(aDh, (ph & bit) ? 1u : 0u);
+            ph ^= bit;
             tc_fence_after();
-#pragma unroll
-            for (int pc = 0; pc < NCOL / EC; ++pc) {
-                uint32_t w[EC], hi2[EC / 2], lo2[EC / 2];
-                tmem_ld_n<EC>(tD + NCOL * h + EC * pc, w);
-                tc_wait_ld();
-                epilogue_split_v2<EC / 8, false, 0>(w, hi2, lo2);
-                tmem_st_n<EC / 2>(tD + 64 + (NCOL / 2) * h + (EC / 2) * pc, hi2);
-                tmem_st_n<EC / 2>(tD + 96 + (NCOL / 2) * h + (EC / 2) * pc, lo2);
-            }
+            if (nch == 3) epi_split_chunks<3>(tD, cb0);
+            else if (nch == 4) epi_split_chunks<4>(tD, cb0);
+            else epi_split_chunks<2>(tD, cb0);
             if (layer < MEMS_NLAYER_H) {                   // bias of hidden layer `layer` (the next GEMM) into D
-                const float4* b4 = reinterpret_cast<const float4*>(cm->tcbias + layer * MEMS_WIDTH + NCOL * h);
-#pragma unroll
-                for (int c8 = 0; c8 < NCOL / 8; ++c8) {
-                    const float4 u = __ldg(b4 + 2 * c8), v = __ldg(b4 + 2 * c8 + 1);
+                for (int c8 = 0; c8 < nch; ++c8) {
+                    const float4* b4 = reinterpret_cast<const float4*>(cm->tcbias + layer * MEMS_WIDTH + cb0 + 8 * c8);
+                    const float4 u = __ldg(b4), v = __ldg(b4 + 1);
                     const uint32_t bw[8] = {__float_as_uint(u.x), __float_as_uint(u.y), __float_as_uint(u.z), __float_as_uint(u.w),
                                             __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
-                    tmem_st8(tD + NCOL * h + 8 * c8, bw);
+                    tmem_st8(tD + cb0 + 8 * c8, bw);
                 }
             }
             tc_wait_st();
             tc_fence_before();
             mbar_arrive_a(aAh);
         }
+    };
+    if (!is_tail) {
+        tanh_layers(1u);
         mbar_wait_a(aDh, ph & 1u);                         // output layer complete: relay to the tail warps
         ph ^= 1u;
         tc_fence_after();
@@ -484,6 +516,10 @@ __device__ __forceinline__ void tc_coarse_group(TcSmem& sm, GroupSmem& gs, int g
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(&gs.bar_At[0]);
+        if (MEMS_TAIL_SHARE) {
+            tanh_layers(4u);
+            ph ^= 4u;                                       // the output layer's phase of bar_Dh[0], observed through bar_X below
+        }
         mbar_wait(&gs.bar_X[0], ph & 1u);
         ph ^= 1u;
         tc_fence_after();
@@ -554,7 +590,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
         for (int g = 0; g < NGROUP; ++g) {
             for (int s = 0; s < GSLOT; ++s) {
                 mbar_init(&sm.grp[g].bar_At[s], TTHREADS);
-                mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS);
+                mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS + (MEMS_TAIL_SHARE ? TTHREADS : 0));
                 mbar_init(&sm.grp[g].bar_Dh[s], 1);
                 mbar_init(&sm.grp[g].bar_X[s], HTHREADS);
             }

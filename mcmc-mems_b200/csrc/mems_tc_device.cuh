@@ -59,7 +59,14 @@ namespace {
 // threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
 constexpr int NGROUP = 2;
 constexpr int GSLOT = 2;                       // tile slots per group
+#ifndef MEMS_TAIL_SHARE
+#define MEMS_TAIL_SHARE 0                      // 1: the tail warps also take the last 16 accumulator columns of every tile-layer
+#endif                                         //    (24 / 24 / 16 split: six epilogue warps per SM sub-partition instead of four).
+                                               //    Measured equal (41.3 vs 41.35 M chain-steps/s, parity green): the hidden warps do
+                                               //    not lack latency hiding, they wait for the slowest of their group at every hand-off
 constexpr int NH = 2;                          // column halves of the hidden warps
+constexpr int HCOLS = MEMS_TAIL_SHARE ? 24 : 32;   // accumulator columns per hidden thread
+constexpr int TCOLS = 64 - NH * HCOLS;         // ... per tail thread
 constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
 constexpr int TTHREADS = 128;                  // tail threads per group
 constexpr int GTHREADS = HTHREADS + TTHREADS;  // 384: the threads of a group that meet at group barriers
