@@ -1,4 +1,14 @@
-"""CPU tests: the oracle against every pin the reference holds for this path."""
+"""CPU tests: the oracle against every pin the reference holds for this path.
+
+What is pinned how (the reference's own stack -- TensorFlow 2.7.1, CUQIpy 0.8.0 -- cannot be installed here):
+  * K1 is the only DIRECT TensorFlow output in the reference tree, and it is for the FFT model; the time-series surrogates
+    (`model_VoltageSignal.keras`) go through the same HDF5 reader, layer order, `[in, out]` kernel layout, tanh / linear code, so
+    they are pinned TRANSITIVELY by K1, plus the held-out simulation they were trained to match;
+  * the CUQIpy semantics (MH.single_update, MH._sample_adapt, Gaussian.logd, Uniform.logpdf) are RECALLED from the library
+    (SURVEY.md App. A), not read from vendored source; they are pinned STATISTICALLY by the acceptance rates / adapted scales
+    the notebooks printed (K3) and the spread of the stored chains (K4);
+  * component-wise MH and delayed acceptance have no reference artefact at all: parity unpinned (oracle definition only).
+"""
 import glob
 import os
 
@@ -11,7 +21,8 @@ from oracle import (batched_forward, cwmh_sample, da_sample, decide, gaussian_lo
 
 
 def test_k1_tf_float32_known_answer():
-    """K1: TF float32 predictions printed in surrogate_fft.ipynb cell 11 (10 rows x 15 outputs)."""
+    """K1: TF float32 predictions printed in surrogate_fft.ipynb cell 11 (10 rows x 15 outputs) -- the direct pin of the loader
+    and the Dense/tanh stack; the time-series models are pinned transitively (same code path)."""
     d = np.load(os.path.join(helpers.GOLDEN, "k1_fft.npz"))
     pred = mlp_forward(helpers.layers_of(d), d["X_test_scaled"])
     assert pred.shape == (10, 15) and pred.dtype == np.float32
