@@ -31,8 +31,14 @@ def test_abi_argument_errors_without_gpu(lib_built):
     bad = _lib.MemsConfig(3, 150, 4, 0, 0, 129)
     assert L.mems_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert L.mems_run(None, 1, 0, 1, None, None, None) == -1
+    # device-diagnostics entry points: argument checks and the host-only capacity rule (power of two, >= one 2048-key tile)
+    assert [L.mems_sort_capacity(n) for n in (-1, 0, 1, 2048, 2049, 70001)] == [0, 2048, 2048, 2048, 4096, 131072]
+    assert L.mems_sort_f64(0, None, -1, None) == -1 and L.mems_sort_f64(0, None, 1, None) == 0      # n <= 1: nothing to do
+    assert L.mems_rank_normalize(0, None, 0, None, 5, None, None) == -1
+    assert L.mems_ess_geyer(0, None, 1, 8, 100, 4, None, None, None) == -1
     import torch
     if not torch.cuda.is_available():
+        assert L.mems_sort_f64(0, ctypes.c_void_p(16), 5, None) == -4 and b"no CPU fallback" in L.mems_last_error()
         ok = _lib.MemsConfig(3, 150, 4, 0, 0, 0)
         assert L.mems_create(ctypes.byref(ok), ctypes.byref(h)) == -4      # no device, no CPU fallback
         assert b"no CPU fallback" in L.mems_last_error()
