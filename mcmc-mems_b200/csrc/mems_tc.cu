@@ -22,6 +22,35 @@
 // Reference semantics: see mems_common.cuh header (src/InverseProblems/utils.py:30-40 etc.).
 #include "mems_tc_device.cuh"
 
+#ifndef MEMS_TRACE
+#define MEMS_TRACE 0           // 1 (development builds only): block 0 records a timeline of its hand-offs, read with mems_trace_read
+#endif
+#if MEMS_TRACE
+__device__ unsigned long long g_trace[32][8192];
+__device__ unsigned int g_trace_n[32];
+__device__ __forceinline__ void trace_ev(int tag) {         // ~40 cycles: clock read, shared-memory counter, fire-and-forget store
+    __shared__ unsigned int s_n[32];
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        const int w = threadIdx.x >> 5;
+        unsigned int n = s_n[w];
+        if (n >= 0x80000000u || n == 0xFFFFFFFFu) n = 0;      // (uninitialised shared memory is handled by the marker below)
+        if ((tag & 15) == 15) { s_n[w] = 0; return; }         // kind 15: reset at kernel start
+        if (n < 8192u) { g_trace[w][n] = ((unsigned long long)clock64() << 12) | (unsigned long long)(tag & 0xFFF); s_n[w] = n + 1u; g_trace_n[w] = n + 1u; }
+    }
+}
+extern "C" int mems_trace_read(unsigned long long* host_buf, unsigned int* host_n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_buf, g_trace, sizeof(g_trace));
+    cudaMemcpyFromSymbol(host_n, g_trace_n, sizeof(g_trace_n));
+    unsigned int zero[32] = {0};
+    cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
+    return 0;
+}
+#define TRACE(kind, s, layer) trace_ev((kind) | ((s) << 4) | ((layer) << 6))
+#else
+#define TRACE(kind, s, layer)
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -88,10 +117,10 @@ __device__ __forceinline__ void issue_coarse_pass(GroupSmem& gs, uint32_t d, con
             }
         }
         __syncwarp();
-        if (layer == 0) { mbar_wait_a(aAt, (ph >> 2) & 1u); ph ^= 4u; }
+        if (layer == 0) { mbar_wait_a(aAt, (ph >> GSLOT) & 1u); ph ^= (1u << GSLOT); }
         else { mbar_wait_a(aAh, ph & 1u); ph ^= 1u; }
-        mbar_wait_a(aW, (ph >> 5) & 1u);
-        ph ^= 32u;
+        mbar_wait_a(aW, (ph >> (2 * GSLOT + 1)) & 1u);
+        ph ^= (1u << (2 * GSLOT + 1));
         tc_fence_after();
         if (elect_one()) {
             const uint64_t bA = make_desc(stageA), bB = make_desc(stageB);
@@ -126,14 +155,14 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                                                 uint32_t stageA = 0u) {
     const uint32_t wimg = smem_u32(sm.wimg);
     const uint32_t base = __shfl_sync(0xffffffffu, sm.tmem_base, 0) + (uint32_t)(g * GSLOT * 128);
-    uint32_t ph = 0;                  // bits 0,1: bar_Ah parity per slot; bits 2,3: bar_At; bit 4: bar_S; bit 5: bar_W
+    uint32_t ph = 0;                  // bits [0, GSLOT): bar_Ah parity per slot; [GSLOT, 2 GSLOT): bar_At; then bar_S, bar_W
     uint32_t nD = 0;                  // commits issued on slot 0 so far (phase of bar_Dh[0] the next commit completes)
     const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
     const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
     const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
     for (;;) {
-        mbar_wait(&gs.bar_S[slot0], (ph >> 4) & 1u);
-        ph ^= 16u;
+        mbar_wait(&gs.bar_S[slot0], (ph >> (2 * GSLOT)) & 1u);
+        ph ^= (1u << (2 * GSLOT));
         const int n_tiles = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(&gs.ctrl_tiles), 0);
         if (n_tiles < 0) break;
         if (n_tiles == COARSE_TILES) {                                   // only the issuer of slot 0 is woken for a coarse pass
@@ -147,18 +176,21 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                 for (int k = 0; k < NSLOT; ++k) {
                     const int s = slot0 + k;
                     if (t0 + s < n_tiles) {
+                        TRACE(4, s, layer);
                         if (layer == 0) {
-                            mbar_wait_a(aAt + 8 * s, (ph >> (2 + s)) & 1u);
-                            ph ^= (4u << s);
+                            mbar_wait_a(aAt + 8 * s, (ph >> (GSLOT + s)) & 1u);
+                            ph ^= (1u << (GSLOT + s));
                         } else {
                             mbar_wait_a(aAh + 8 * s, (ph >> s) & 1u);
                             ph ^= (1u << s);
                         }
+                        TRACE(5, s, layer);
                         tc_fence_after();
                         if (elect_one()) {
                             issue_layer(wimg, base + s * 128, layer);
                             umma_commit_a(aDh + 8 * s);
                         }
+                        TRACE(6, s, layer);
                         if (s == 0) ++nD;
                         __syncwarp();
                     }
@@ -263,7 +295,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
     const int tpt = 128 / nce;                        // time points per tile
     const int Tn = (T + stride - 1) / stride;         // time points of this pass: t = 0, stride, 2*stride, ...
     const int n_tiles = DENSE ? (nce * Tn + 127) / 128 : (Tn + tpt - 1) / tpt;
-    const int n_pairs = (n_tiles + 1) >> 1;
+    const int n_rounds = (n_tiles + GSLOT - 1) / GSLOT;      // every slot takes one tile per round
     const uint32_t tD0 = sm.tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * GSLOT * 128);
     if (gt == 0) announce_tiles(gs, n_tiles);
 
@@ -273,15 +305,17 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         const uint32_t aDh = keep_in_register(smem_u32(&gs.bar_Dh[0]));
         const uint32_t aAh = aDh - (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_Ah));
         const uint32_t aX = aDh + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_Dh));
-        for (int pair = 0; pair < n_pairs; ++pair) {
+        for (int round = 0; round < n_rounds; ++round) {
 #pragma unroll 1
             for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
                 for (int s = 0; s < GSLOT; ++s) {
-                    if (pair * 2 + s < n_tiles) {
+                    if (round * GSLOT + s < n_tiles) {
                         const uint32_t tD = tD0 + s * 128;
+                        TRACE(1, s, layer);
                         mbar_wait_a(aDh + 8 * s, (ph >> s) & 1u);
                         ph ^= (1u << s);
+                        TRACE(2, s, layer);
                         tc_fence_after();
                         if (layer < MEMS_HIDDEN - 1) {
                             epi_split_chunks<HCOLS / 8>(tD, cb0);
@@ -298,10 +332,12 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                             tc_wait_st();
                             tc_fence_before();
                             mbar_arrive_a(aAh + 8 * s);
+                            TRACE(3, s, layer);
                         } else {                               // last tanh layer . output weights: partial dot to the tail warps
                             gs.xchg[s][gt >> 7][row] = epi_dot_chunks<HCOLS / 8>(tD, cb0, sm.w7);
                             tc_fence_before();                 // the accumulator has been read: the slot may be restaged
                             mbar_arrive_a(aX + 8 * s);         // release: the store above is visible to the tail warps
+                            TRACE(3, s, layer);
                         }
                     }
                 }
@@ -350,10 +386,14 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         // a tile's output is complete (own columns in `own`, the hidden warps' partial dots in xchg): residual, then the
         // layer-1 operand of the slot's next tile
         auto finish_tile = [&](int s, int tile, float own) {
+            TRACE(7, s, 0);
             mbar_wait_a(aX + 8 * s, (ph >> s) & 1u);
             ph ^= (1u << s);
+            TRACE(8, s, 0);
             tc_fence_after();                              // the hidden warps' accumulator reads precede the restaging below
-            const float o = gs.xchg[s][0][row] + gs.xchg[s][1][row] + own + sm.b7;
+            float o = own + sm.b7;
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh) o += gs.xchg[s][hh][row];
             if (DENSE) {
                 const int f = tile * 128 + row;
                 const int ti = f / nce;
@@ -369,7 +409,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     if (r0 < 0) r0 += nce;
                     for (int rr = r0; rr < 128; rr += nce) Sp += gs.R2[s][rr];
                 }
-                // R2[s] is written again two tiles later, behind another barrier of all tail threads on R2[1 - s]
+                // R2[s] is written again GSLOT tiles later, behind the barriers of all tail threads on the other slots' R2
             } else {
                 const int ti = tile * tpt + sub;
                 const int t = ti * stride;
@@ -382,22 +422,23 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             // this slot's D and A are free again: stage the layer-1 operand of its next tile
             const int nt = tile + GSLOT;
             if (nt < n_tiles) stage_tile(s, nt);
+            TRACE(9, s, 0);
         };
 #pragma unroll
         for (int s = 0; s < GSLOT; ++s)
             if (s < n_tiles) stage_tile(s, s);
 
-        for (int pair = 0; pair < n_pairs; ++pair) {
+        for (int round = 0; round < n_rounds; ++round) {
             if (MEMS_TAIL_SHARE) {
 #pragma unroll 1
                 for (int layer = 0; layer < MEMS_HIDDEN; ++layer) {
 #pragma unroll
                     for (int s = 0; s < GSLOT; ++s) {
-                        const int tile = pair * 2 + s;
+                        const int tile = round * GSLOT + s;
                         if (tile < n_tiles) {
                             const uint32_t tD = tD0 + s * 128;
-                            mbar_wait_a(aDh + 8 * s, (ph >> (2 + s)) & 1u);
-                            ph ^= (4u << s);
+                            mbar_wait_a(aDh + 8 * s, (ph >> (GSLOT + s)) & 1u);
+                            ph ^= (1u << (GSLOT + s));
                             tc_fence_after();
                             if (layer < MEMS_HIDDEN - 1) {
                                 epi_split_chunks<TCOLS / 8>(tD, 2 * HCOLS);
@@ -415,7 +456,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
             } else {
 #pragma unroll 1
                 for (int s = 0; s < GSLOT; ++s) {
-                    const int tile = pair * 2 + s;
+                    const int tile = round * GSLOT + s;
                     if (tile < n_tiles) finish_tile(s, tile, 0.0f);
                 }
             }
@@ -517,8 +558,8 @@ __device__ __forceinline__ void tc_coarse_group(TcSmem& sm, GroupSmem& gs, int g
         tc_fence_before();
         mbar_arrive(&gs.bar_At[0]);
         if (MEMS_TAIL_SHARE) {
-            tanh_layers(4u);
-            ph ^= 4u;                                       // the output layer's phase of bar_Dh[0], observed through bar_X below
+            tanh_layers(1u << GSLOT);
+            ph ^= (1u << GSLOT);                            // the output layer's phase of bar_Dh[0], observed through bar_X below
         }
         mbar_wait(&gs.bar_X[0], ph & 1u);
         ph ^= 1u;
@@ -642,6 +683,7 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
     float* s_ts = reinterpret_cast<float*>(s_yobs + pb.c.T);
     tc_prologue(sm, pb, s_yobs, s_ts);
 
+    TRACE(15, 0, 0);
     const int T = sm.c.T, nc = ra.nc;
     const int nbatch = (ch.C + nc - 1) / nc;
     int g, gt;
@@ -673,14 +715,17 @@ tc_run_kernel(const MemsProblem* __restrict__ pbp, MemsChains ch, MemsRunArgs ra
                     if (any && batch_pass_is_coarse_model(ra, sub) && ra.coarse_tc)   // DA first stage on the FFT surrogate
                         tc_coarse_group<P>(sm, gs, g, gt, ra.coarse, T, ph);
                     else if (any && batch_pass_is_coarse_model(ra, sub))   // ... on CUDA cores when the staging blocks do not fit
-                        coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, coarse_scratch(gs.cb), gt,
+                        coarse_fft_pass(ra.coarse, P, T, &gs.cb.xp[0][0], MEMS_NCMAX, gs.map, gs.nlive, gs.Sfin, coarse_scratch(gs), gt,
                                         GTHREADS, [g] { group_bar_sync(g); });
                     else if (any) {
                         // dense packing when it saves tiles (n_live does not divide 128 well)
                         const int stride = batch_pass_stride(ra, sub);
                         const int Tn = (T + stride - 1) / stride, tpt = 128 / gs.nlive;
                         if (gt == 0) atomicAdd(ch.rows_eval, (unsigned long long)gs.nlive * (unsigned long long)Tn);
-                        if ((gs.nlive * Tn + 127) / 128 < (Tn + tpt - 1) / tpt)
+                        // (a dense tile costs the tail warps more -- every row changes its chain from tile to tile -- so the packing
+                        //  must save more than MEMS_DENSE_MIN_SAVING percent of the tiles to be chosen)
+                        const int t_dense = (gs.nlive * Tn + 127) / 128, t_plain = (Tn + tpt - 1) / tpt;
+                        if (100 * t_dense < (100 - MEMS_DENSE_MIN_SAVING) * t_plain)
                             tc_eval_group<P, true>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
                         else
                             tc_eval_group<P, false>(sm, gs, g, gt, s_yobs, s_ts, T, stride, nc, ncv, true, nullptr, c0, ph);
@@ -838,7 +883,7 @@ int mems_tc_max_time_points(size_t smem_optin) {
     return (int)((smem_optin - fixed) / (sizeof(double) + sizeof(float)));
 }
 
-// Chains per group batch (any value 1..128): minimise (waves of batches over the 2*SMs groups) x (tile pairs per step).
+// Chains per group batch (any value 1..128): minimise (waves of batches over the NGROUP*SMs groups) x (tile rounds per step).
 int mems_tc_choose_nc(int C, int T, int sm_count) {
     int best = 1;
     long long best_cost = -1;
@@ -847,7 +892,7 @@ int mems_tc_choose_nc(int C, int T, int sm_count) {
         const long long waves = (nbatch + (long long)NGROUP * sm_count - 1) / ((long long)NGROUP * sm_count);
         const int tpt = 128 / nc;
         const long long tiles = (T + tpt - 1) / tpt;
-        const long long cost = waves * ((tiles + 1) / 2) * 2;
+        const long long cost = waves * ((tiles + GSLOT - 1) / GSLOT) * GSLOT;
         if (best_cost < 0 || cost <= best_cost) { best_cost = cost; best = nc; }
     }
     return best;

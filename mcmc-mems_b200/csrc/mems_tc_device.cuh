@@ -22,6 +22,9 @@
 #define MEMS_BIAS_PRELOAD 0    // 1: the hidden warps write the next layer's bias into the accumulator (tcgen05.st) instead of the
 #endif                         //    shared-memory-operand bias MMA (13 -> 12 MMAs per layer).  Measured: 40.1 vs 41.4 M chain-steps/s --
                                //    the 12 extra epilogue instructions per thread cost more than the 75 tensor cycles save
+#ifndef MEMS_DENSE_MIN_SAVING
+#define MEMS_DENSE_MIN_SAVING 6    // percent of a pass's tiles the dense packing has to save before it is used
+#endif
 #ifndef MEMS_EX2_MIX
 #define MEMS_EX2_MIX 0         // (round-1 arithmetic, micro-benchmarks only) share of exponentials on the FMA pipe
 #endif
@@ -57,15 +60,20 @@ namespace {
 // Hand-offs are mbarriers (tail -> issuer -> hidden -> issuer ... -> tail); groups never synchronise with each other, so
 // one group's accept/reject section overlaps the other group's tensor work.  The first min(n_chains, 128) hidden
 // threads of a group also do the per-chain Metropolis-Hastings bookkeeping between passes.
-constexpr int NGROUP = 2;
-constexpr int GSLOT = 2;                       // tile slots per group
+#ifndef MEMS_NGROUP
+#define MEMS_NGROUP 2                          // 2: two groups x two tile slots; 1: one group of all hidden warps over four slots
+#endif                                         //    (a slot's MMA batch then has three epilogues to hide behind instead of one)
+constexpr int NGROUP = MEMS_NGROUP;
+constexpr int GSLOT = 4 / NGROUP;              // tile slots per group: NGROUP * GSLOT * 128 = the 512 TMEM columns
+static_assert(NGROUP == 1 || NGROUP == 2, "one or two groups");
 #ifndef MEMS_TAIL_SHARE
 #define MEMS_TAIL_SHARE 0                      // 1: the tail warps also take the last 16 accumulator columns of every tile-layer
 #endif                                         //    (24 / 24 / 16 split: six epilogue warps per SM sub-partition instead of four).
                                                //    Measured equal (41.3 vs 41.35 M chain-steps/s, parity green): the hidden warps do
                                                //    not lack latency hiding, they wait for the slowest of their group at every hand-off
-constexpr int NH = 2;                          // column halves of the hidden warps
-constexpr int HCOLS = MEMS_TAIL_SHARE ? 24 : 32;   // accumulator columns per hidden thread
+constexpr int NH = 4 / NGROUP;                 // column parts of the hidden warps: 16 hidden warps = NGROUP x 4 lane quarters x NH
+static_assert(!MEMS_TAIL_SHARE || NH == 2, "the 24 / 24 / 16 split is defined for two column halves");
+constexpr int HCOLS = MEMS_TAIL_SHARE ? 24 : 64 / NH;   // accumulator columns per hidden thread
 constexpr int TCOLS = 64 - NH * HCOLS;         // ... per tail thread
 constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
 constexpr int TTHREADS = 128;                  // tail threads per group
@@ -106,6 +114,14 @@ constexpr int COARSE_STAGE_BYTES = NGROUP * BLK + 1024;   // extra dynamic share
 static_assert(offsetof(ChainBatch, scale_cw) % 1024 == 0, "stage B must be 1024-byte aligned inside the batch");
 static_assert(sizeof(double) * 2 * MEMS_PMAX * MEMS_NCMAX >= BLK, "stage B does not fit in scale_cw + lambda_cw");
 
+// Scratch of the coarse (FFT surrogate) first stage of delayed acceptance: 2*(2*GTHREADS/64)*64 floats.  It lives in the
+// component-wise sampler's per-chain scale arrays of the batch (scale_cw, lambda_cw), which delayed acceptance never uses.
+constexpr int COARSE_SCRATCH_FLOATS = 2 * (2 * GTHREADS / 64) * MEMS_WIDTH;
+static_assert(GTHREADS % 64 == 0, "coarse_fft_pass needs a multiple of 64 threads");
+static_assert(offsetof(ChainBatch, lambda_cw) == offsetof(ChainBatch, scale_cw) + sizeof(double) * MEMS_PMAX * MEMS_NCMAX,
+              "scale_cw and lambda_cw must be adjacent");
+constexpr bool COARSE_SCRATCH_IN_BATCH = sizeof(float) * COARSE_SCRATCH_FLOATS <= 2 * sizeof(double) * MEMS_PMAX * MEMS_NCMAX;
+
 struct alignas(1024) GroupSmem {
     ChainBatch cb;                     // 1024-aligned: cb.scale_cw doubles as a swizzled operand block in the coarse pass
     double Spart[128];                 // per tile row: partial sum of squared residuals over the pass (tail threads)
@@ -114,7 +130,7 @@ struct alignas(1024) GroupSmem {
     unsigned long long bar_Ah[GSLOT];  // hidden -> MMA issuer: A operand of the slot's next layer is in TMEM
     unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of the slot is complete
     unsigned long long bar_X[GSLOT];   // hidden -> tail warps: partial output-layer dots of the slot's tile are in xchg
-    float xchg[GSLOT][NH][128];        // partial output-layer dots of the two column halves
+    float xchg[GSLOT][NH][128];        // partial output-layer dots of the column parts
     unsigned long long bar_S[GSLOT];   // group -> MMA issuer of the slot: ctrl_tiles of the next pass is valid (signalled only when
                                        // the pass has a tile for that slot, or to end: every signalled phase is consumed before the next)
     unsigned long long bar_W;          // bulk copy -> MMA issuer: the coarse model's operand blocks of a layer are staged
@@ -122,15 +138,11 @@ struct alignas(1024) GroupSmem {
     int nlive;                         // chains of the batch that need the coming pass (in the box / promoted)
     double Sfin[MEMS_NCMAX];           // per chain: sum of squared residuals of the pass
     unsigned char map[MEMS_NCMAX];     // compaction: map[k] = batch-local index of the k-th live chain
+    float coarse_scr[COARSE_SCRATCH_IN_BATCH ? 4 : COARSE_SCRATCH_FLOATS];   // CUDA-core coarse pass scratch when cb has no room
 };
-// Scratch of the coarse (FFT surrogate) first stage of delayed acceptance: 2*(2*GTHREADS/64)*64 floats.  It lives in the
-// component-wise sampler's per-chain scale arrays of the batch (scale_cw, lambda_cw), which delayed acceptance never uses.
-constexpr int COARSE_SCRATCH_FLOATS = 2 * (2 * GTHREADS / 64) * MEMS_WIDTH;
-static_assert(GTHREADS % 64 == 0, "coarse_fft_pass needs a multiple of 64 threads");
-static_assert(offsetof(ChainBatch, lambda_cw) == offsetof(ChainBatch, scale_cw) + sizeof(double) * MEMS_PMAX * MEMS_NCMAX,
-              "scale_cw and lambda_cw must be adjacent");
-static_assert(sizeof(float) * COARSE_SCRATCH_FLOATS <= 2 * sizeof(double) * MEMS_PMAX * MEMS_NCMAX, "coarse scratch does not fit");
-__device__ __forceinline__ float* coarse_scratch(ChainBatch& cb) { return reinterpret_cast<float*>(&cb.scale_cw[0][0]); }
+__device__ __forceinline__ float* coarse_scratch(GroupSmem& gs) {
+    return COARSE_SCRATCH_IN_BATCH ? reinterpret_cast<float*>(&gs.cb.scale_cw[0][0]) : gs.coarse_scr;
+}
 
 struct TcSmem {
     __align__(1024) unsigned char wimg[NBLK * BLK];
