@@ -160,6 +160,9 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
     const uint32_t aAt = keep_in_register(smem_u32(&gs.bar_At[0]));
     const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
     const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
+    const uint32_t aX = aAt + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_At));
+    const uint32_t aF = aAt + (uint32_t)(offsetof(GroupSmem, bar_F) - offsetof(GroupSmem, bar_At));
+    uint32_t xph = 0;                 // bit s: parity of the number of tiles issued on slot s = phases of bar_X[s] started so far
     for (;;) {
         mbar_wait(&gs.bar_S[slot0], (ph >> (2 * GSLOT)) & 1u);
         ph ^= (1u << (2 * GSLOT));
@@ -167,6 +170,7 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
         if (n_tiles < 0) break;
         if (n_tiles == COARSE_TILES) {                                   // only the issuer of slot 0 is woken for a coarse pass
             issue_coarse_pass(gs, base, cimg, stageA, ph, nD, aAt, aAh, aDh);
+            xph ^= 1u;                                                   // the coarse pass completes one phase of bar_X[0]
             continue;
         }
         for (int t0 = 0; t0 < n_tiles; t0 += GSLOT) {
@@ -180,6 +184,8 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                         if (layer == 0) {
                             mbar_wait_a(aAt + 8 * s, (ph >> (GSLOT + s)) & 1u);
                             ph ^= (1u << (GSLOT + s));
+                            // prestaged operands arrive before the previous tile of the slot has been read out of the accumulator
+                            if (MEMS_PRESTAGE && t0 > 0) mbar_wait_a(aX + 8 * s, ((xph >> s) & 1u) ^ 1u);
                         } else {
                             mbar_wait_a(aAh + 8 * s, (ph >> s) & 1u);
                             ph ^= (1u << s);
@@ -189,7 +195,9 @@ __device__ __forceinline__ void mma_issuer_loop(TcSmem& sm, GroupSmem& gs, int g
                         if (elect_one()) {
                             issue_layer(wimg, base + s * 128, layer);
                             umma_commit_a(aDh + 8 * s);
+                            if (MEMS_PRESTAGE && layer == MEMS_HIDDEN - 1) umma_commit_a(aF + 8 * s);
                         }
+                        if (layer == MEMS_HIDDEN - 1) xph ^= (1u << s);   // one more tile of this slot will complete a phase of bar_X
                         TRACE(6, s, layer);
                         if (s == 0) ++nD;
                         __syncwarp();
@@ -353,6 +361,7 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
         const uint32_t aX = aAt + (uint32_t)(offsetof(GroupSmem, bar_X) - offsetof(GroupSmem, bar_At));
         const uint32_t aDh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Dh) - offsetof(GroupSmem, bar_At));
         const uint32_t aAh = aAt + (uint32_t)(offsetof(GroupSmem, bar_Ah) - offsetof(GroupSmem, bar_At));
+        const uint32_t aF = aAt + (uint32_t)(offsetof(GroupSmem, bar_F) - offsetof(GroupSmem, bar_At));
         uint32_t a1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a1[i] = 0u;
@@ -419,9 +428,9 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     Sp = fma(r, r, Sp);
                 }
             }
-            // this slot's D and A are free again: stage the layer-1 operand of its next tile
+            // this slot's D and A are free again: stage the layer-1 operand of its next tile (unless it was staged early)
             const int nt = tile + GSLOT;
-            if (nt < n_tiles) stage_tile(s, nt);
+            if (!MEMS_PRESTAGE && nt < n_tiles) stage_tile(s, nt);
             TRACE(9, s, 0);
         };
 #pragma unroll
@@ -454,6 +463,20 @@ __device__ __forceinline__ void tc_eval_group(TcSmem& sm, GroupSmem& gs, int g, 
                     }
                 }
             } else {
+                if (MEMS_PRESTAGE) {
+                    // the operand columns of a slot are free once its last layer's MMAs have completed (bar_F) -- long before the
+                    // hidden warps have turned that accumulator into the tile's output: the next tile's layer-1 operand goes in now
+#pragma unroll 1
+                    for (int s = 0; s < GSLOT; ++s) {
+                        const int tile = round * GSLOT + s;
+                        if (tile < n_tiles) {
+                            mbar_wait_a(aF + 8 * s, (ph >> (GSLOT + s)) & 1u);
+                            ph ^= (1u << (GSLOT + s));
+                            tc_fence_after();
+                            if (tile + GSLOT < n_tiles) stage_tile(s, tile + GSLOT);
+                        }
+                    }
+                }
 #pragma unroll 1
                 for (int s = 0; s < GSLOT; ++s) {
                     const int tile = round * GSLOT + s;
@@ -634,6 +657,7 @@ __device__ __forceinline__ void tc_prologue(TcSmem& sm, const MemsProblem& pb, d
                 mbar_init(&sm.grp[g].bar_Ah[s], HTHREADS + (MEMS_TAIL_SHARE ? TTHREADS : 0));
                 mbar_init(&sm.grp[g].bar_Dh[s], 1);
                 mbar_init(&sm.grp[g].bar_X[s], HTHREADS);
+                mbar_init(&sm.grp[g].bar_F[s], 1);
             }
             for (int s = 0; s < GSLOT; ++s) mbar_init(&sm.grp[g].bar_S[s], 1);
             mbar_init(&sm.grp[g].bar_W, 1);

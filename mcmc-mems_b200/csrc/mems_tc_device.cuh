@@ -22,6 +22,10 @@
 #define MEMS_BIAS_PRELOAD 0    // 1: the hidden warps write the next layer's bias into the accumulator (tcgen05.st) instead of the
 #endif                         //    shared-memory-operand bias MMA (13 -> 12 MMAs per layer).  Measured: 40.1 vs 41.4 M chain-steps/s --
                                //    the 12 extra epilogue instructions per thread cost more than the 75 tensor cycles save
+#ifndef MEMS_PRESTAGE
+#define MEMS_PRESTAGE 0        // 1: the tail warps stage a slot's next layer-1 operand as soon as the last layer's MMAs have completed
+#endif                         //    (second commit -> bar_F), not after the tile's output: the staging leaves the slot's critical path.
+                               //    Measured equal (41.0-41.4 vs 41.2-41.5 M chain-steps/s, parity green): see DESIGN.md, power
 #ifndef MEMS_DENSE_MIN_SAVING
 #define MEMS_DENSE_MIN_SAVING 6    // percent of a pass's tiles the dense packing has to save before it is used
 #endif
@@ -73,6 +77,7 @@ static_assert(NGROUP == 1 || NGROUP == 2, "one or two groups");
                                                //    not lack latency hiding, they wait for the slowest of their group at every hand-off
 constexpr int NH = 4 / NGROUP;                 // column parts of the hidden warps: 16 hidden warps = NGROUP x 4 lane quarters x NH
 static_assert(!MEMS_TAIL_SHARE || NH == 2, "the 24 / 24 / 16 split is defined for two column halves");
+static_assert(!(MEMS_TAIL_SHARE && MEMS_PRESTAGE), "early staging is implemented for tail warps without an epilogue share");
 constexpr int HCOLS = MEMS_TAIL_SHARE ? 24 : 64 / NH;   // accumulator columns per hidden thread
 constexpr int TCOLS = 64 - NH * HCOLS;         // ... per tail thread
 constexpr int HTHREADS = 128 * NH;             // hidden-layer threads per group
@@ -129,7 +134,9 @@ struct alignas(1024) GroupSmem {
     unsigned long long bar_At[GSLOT];  // tail -> MMA issuer: layer-1 operand of the slot's next tile is in TMEM
     unsigned long long bar_Ah[GSLOT];  // hidden -> MMA issuer: A operand of the slot's next layer is in TMEM
     unsigned long long bar_Dh[GSLOT];  // tensor core -> hidden warps: accumulator of the slot is complete
-    unsigned long long bar_X[GSLOT];   // hidden -> tail warps: partial output-layer dots of the slot's tile are in xchg
+    unsigned long long bar_X[GSLOT];   // hidden -> tail warps (and the MMA issuer): partial output-layer dots of the slot's tile are in
+                                       // xchg, the accumulator has been read
+    unsigned long long bar_F[GSLOT];   // tensor core -> tail warps: the last layer's MMAs are done, the operand columns may be restaged
     float xchg[GSLOT][NH][128];        // partial output-layer dots of the column parts
     unsigned long long bar_S[GSLOT];   // group -> MMA issuer of the slot: ctrl_tiles of the next pass is valid (signalled only when
                                        // the pass has a tile for that slot, or to end: every signalled phase is consumed before the next)
