@@ -296,3 +296,33 @@ def test_notebook_workflow_posterior_agrees_with_oracle_within_mc_error():
     assert abs(many.acc_rate.mean() - np.mean(pr["acc"])) <= 0.02 and abs(np.median(many.scale) / np.mean(pr["scale"]) - 1.0) <= 0.10
     assert abs(many.acc_rate.mean() - np.mean([r[2] for r in o])) < 0.01
     cuqi_compat.close_engines()
+
+
+# ----------------------------------------------------------------------------- long traces: coarse stage falls back to CUDA cores
+def test_fft_delayed_acceptance_on_a_long_trace_falls_back_to_the_cuda_core_coarse_stage():
+    """T = 700: the staging blocks of the tensor-core coarse pass no longer fit next to the resident fine weights and the
+    observation / time columns, so the same kernel scores the FFT surrogate on CUDA cores (no switch to flip): every
+    two-stage decision against the oracle, on a Q-factor problem whose time grid is resampled (synthetic long-trace
+    configuration, as BASELINE.json's Z trace)."""
+    from mcmc_mems_b200 import engine as E
+    pb = dict(helpers.load_problem("qfactor"))
+    T = 700
+    pb["time"] = np.linspace(pb["time"][0], pb["time"][-1], T)
+    f = np.asarray(helpers.oracle_forward(pb)(pb["x_true"]), np.float64)
+    pb["y_obs"] = f + np.sqrt(pb["sigma2"]) * np.random.default_rng(0).standard_normal(T)
+    cf = helpers.fft_coarse()
+    coarse = helpers.coarse_ll_fn(pb, cf)
+    C, S = 40, 10
+    rng, L, x0 = _inputs(pb, C, S, 41, jitter=0.3)
+    xi = rng.standard_normal((S, C, 4)) @ L.T
+    log_u = np.log(rng.random((S, C, 2)))
+    eng = helpers.engine(pb, C, 1)
+    eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+    eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+    eng.init_chains(x0, scale0=0.3)
+    smp, llp, dec = eng.run_explicit(xi.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
+    res = helpers.check_explicit_da(pb, x0, 0.3, 0, xi, log_u, smp.cpu().numpy(), llp.cpu().numpy(), dec.cpu().numpy(),
+                                    BAND[1], coarse_ll=coarse)
+    assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
+    assert res["promoted"] > 0
+    eng.close()
