@@ -482,8 +482,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sweep_1M", choices=["sweep_1M", "geometric_4096"])
     ap.add_argument("--chains", type=int, default=0, help="sweep_1M: chains in total (default 1048576); geometric_4096: chains per GPU (default 4096)")
-    ap.add_argument("--inner", type=int, default=0, help="MH updates per bench step (default: 16 for sweep_1M, 256 for geometric_4096)")
-    ap.add_argument("--thin", type=int, default=0, help="keep every thin-th update (default: 16 / 64)")
+    ap.add_argument("--inner", type=int, default=0, help="MH updates per bench step (default: 32 for sweep_1M, 256 for geometric_4096)")
+    ap.add_argument("--thin", type=int, default=0, help="keep every thin-th update (default: 32 / 64)")
     ap.add_argument("--time-points", type=int, default=150)
     ap.add_argument("--path", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -498,9 +498,9 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.inner <= 0:
-        args.inner = 16 if args.workload == "sweep_1M" else 256
+        args.inner = 32 if args.workload == "sweep_1M" else 256
     if args.thin <= 0:
-        args.thin = 16 if args.workload == "sweep_1M" else 64
+        args.thin = 32 if args.workload == "sweep_1M" else 64
     _protect_stdout()
     if args.impl == "reference":
         run_reference(args)
