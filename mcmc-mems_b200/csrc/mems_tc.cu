@@ -14,10 +14,16 @@
 //             accumulator is directly the exp2 argument of tanh(z) = 1 - 2/(2^(2z*log2 e) + 1).
 //   layer 1   the (P+1)->64 layer is a K=32 MMA over three-way-split scaled inputs.
 //   pipeline  4 tile slots in flight per SM (4 x 128 TMEM columns) in two independent groups; per group eight
-//             hidden-layer warps, four tail warps (last tanh layer + output layer + residual + next tile's layer-1
-//             operand) and one MMA-issuer warp (mems_tc_device.cuh), handing a slot round by mbarriers.
-//   tail      64->1 output layer, residual against y_obs, squared-sum reduction in FP64, accept/reject
-//             and chain-state update (mems_common.cuh) all happen in the same kernel.
+//             hidden-layer warps (all six tanh epilogues; the last one fused with the 64->1 output layer), four tail
+//             warps (residual + next tile's layer-1 operand + per-chain bookkeeping) and one MMA-issuer warp per slot
+//             (mems_tc_device.cuh), handing a slot round by mbarriers.
+//   tail      residual against y_obs, squared-sum reduction in FP64, accept/reject and chain-state update
+//             (mems_common.cuh) all happen in the same kernel.
+//   coarse    delayed acceptance with the FFT surrogate: its one-row-per-proposal network runs through the same
+//             pipeline, operand blocks streamed from L2 layer by layer (issue_coarse_pass / tc_coarse_group).
+//   switches  MEMS_NGROUP, MEMS_TAIL_SHARE, MEMS_PRESTAGE, MEMS_BIAS_PRELOAD, MEMS_ISSUER_PER_SLOT, MEMS_DENSE_MIN_SAVING:
+//             organisations that were measured against the default (profiles/r02_ab_variants.log);
+//             MEMS_TRACE: development builds that record a hand-off timeline (tools/trace_timeline.py).
 //
 // Reference semantics: see mems_common.cuh header (src/InverseProblems/utils.py:30-40 etc.).
 #include "mems_tc_device.cuh"
