@@ -24,7 +24,6 @@ import torch
 import torch.distributed as dist
 
 from . import _lib, diagnostics
-from ._lib import MemsError
 
 
 def _dist_on(group) -> bool:
@@ -190,7 +189,3 @@ def ess_bulk(samples: torch.Tensor, max_lag: int = 0, group=None, return_truncat
             ess[p], tr[p] = diagnostics.ess_from_autocov(tabn[p, :L] / m_total, half, m_total, var_m)
     return (ess, tr) if return_truncated else ess
 
-
-def require_device(samples: torch.Tensor):
-    if not samples.is_cuda:
-        raise MemsError("diagnostics_device needs device samples")
