@@ -218,16 +218,28 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
 }
 __device__ __forceinline__ bool mbar_try_a(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if MEMS_TRYWAIT_HINT
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
+#ifndef MEMS_POLL_SLEEP_ALL
+#define MEMS_POLL_SLEEP_ALL 0  // > 0 (power experiments only): every waiting warp sleeps this many ns between polls
+#endif
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_a(bar, parity)) {
+        if (MEMS_POLL_SLEEP_ALL > 0) __nanosleep(MEMS_POLL_SLEEP_ALL);
         if (++spins > MEMS_WATCHDOG_SPINS) __trap();
     }
 }

@@ -721,7 +721,7 @@ umma_selftest_kernel(int variant, const __half* __restrict__ A, const __half* __
 // (the product kernel's tensor duty), 2 back to back.  Tells whether tensor-core TMEM / shared-memory traffic slows the
 // epilogue down.  cycles_out[blk] = slowest epilogue thread.
 __global__ void __launch_bounds__(544, 1)
-epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink) {
+epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink, int random_data) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* sB = smem_raw;                    // B (8 KB) + A of the SS-form MMA (16 KB), zero
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + 3 * BLK);
@@ -729,6 +729,14 @@ epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink) {
     volatile int* stop = reinterpret_cast<volatile int*>(smem_raw + 3 * BLK + 32);
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 3 * BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem_raw)[i] = 0u;
+    if (random_data) {
+        // weights in (-0.5, 0.5) and activations in (-1, 1) from a hash: constant (zero) operands hardly toggle the
+        // datapaths, which makes the power drawn by modes 200..202 meaningless (tools/power_probe.py uses 210..212)
+        for (int i = tid; i < BLK / 2; i += blockDim.x) {
+            const unsigned int hsh = (unsigned int)(i + 1) * 2654435761u;
+            reinterpret_cast<__half*>(sB)[i] = __float2half_rn((float)(hsh >> 8) * (1.0f / 16777216.0f) - 0.5f);   // gain > 1: the activations neither die out nor all saturate
+        }
+    }
     if (tid == 0) { mbar_init(bar, 1); *stop = 0; fence_barrier_init(); }
     fence_proxy_async();
     __syncthreads();
@@ -747,7 +755,13 @@ epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink) {
         const uint32_t tl = base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
         uint32_t z[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) z[i] = 0x3c003c00u;
+        for (int i = 0; i < 16; ++i) {
+            z[i] = 0x3c003c00u;
+            if (random_data) {
+                const unsigned int hsh = (unsigned int)(tid * 16 + i + 7) * 2246822519u;
+                z[i] = pack_half2(((float)(hsh >> 16) * (1.0f / 65536.0f)) * 2.0f - 1.0f, ((float)(hsh & 0xFFFFu) * (1.0f / 65536.0f)) * 2.0f - 1.0f);
+            }
+        }
         tmem_st16(tl, z); tmem_st16(tl + 16, z); tmem_st16(tl + 32, z); tmem_st16(tl + 48, z);
         tmem_st16(tl + 64, z); tmem_st16(tl + 80, z); tmem_st16(tl + 96, z); tmem_st16(tl + 112, z);
         tc_wait_st();
@@ -783,7 +797,9 @@ epi_mma_kernel(int duty, int iters, long long* cycles_out, unsigned int* sink) {
             const uint32_t d = base + (uint32_t)(slot * 128);
             if (elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, b + 2 * ks, 1u);
+                // (random data: the first MMA overwrites the accumulator, as in the product -- accumulating for ever saturates
+                //  every tanh and the operands degenerate to +-1 / 0 constants, which understates the power)
+                for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 96 + 8 * ks, b + 2 * ks, (ks > 0 || !random_data) ? 1u : 0u);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma_ts(d, d + 64 + 8 * ks, b + 2 * ks, 1u);
 #pragma unroll
@@ -833,7 +849,12 @@ static int microbench_launch(int mode, int warps, int iters, int blocks, long lo
 #undef MB_CASE
         case 200: case 201: case 202: {          // epilogue (16 warps) + MMA stream: duty = mode - 200
             const size_t smem = 3 * BLK + 64;
-            epi_mma_kernel<<<blocks, 544, smem, st>>>(mode - 200, iters, cycles_out, sink);
+            epi_mma_kernel<<<blocks, 544, smem, st>>>(mode - 200, iters, cycles_out, sink, 0);
+            break;
+        }
+        case 210: case 211: case 212: {          // the same on pseudo-random weights / activations (power measurements)
+            const size_t smem = 3 * BLK + 64;
+            epi_mma_kernel<<<blocks, 544, smem, st>>>(mode - 210, iters, cycles_out, sink, 1);
             break;
         }
         case 100: case 101: {          // MMA rate probe: `warps` carries N/8 (8, 16 or 32), mode 100 = A in TMEM, 101 = A in smem

@@ -51,10 +51,11 @@ def micro(mode, warps, iters):
 
 
 print(f"idle: {sampled(lambda: time.sleep(0.05))[1]:.0f} W")
-for mode, warps, iters, name, per in ((200, 16, 4000, "epilogue alone (16 warps, round-2 arithmetic, no MMAs)", 2),
-                                      (100, 8, 40000, "MMA stream alone (M=128 N=64 K=16, A in TMEM, back to back)", 1),
-                                      (201, 16, 4000, "epilogue + MMA batches at the product kernel's duty", 2),
-                                      (202, 16, 4000, "epilogue + MMA batches back to back", 2)):
+for mode, warps, iters, name, per in ((200, 16, 4000, "epilogue alone, constant data (16 warps, no MMAs)", 2),
+                                      (201, 16, 4000, "epilogue + MMA batches at the product's duty, constant data", 2),
+                                      (210, 16, 4000, "epilogue alone, pseudo-random activations", 2),
+                                      (211, 16, 4000, "epilogue + MMA batches at the product's duty, random data", 2),
+                                      (212, 16, 4000, "epilogue + MMA batches back to back, random data", 2)):
     clk, pw, c = micro(mode, warps, iters)
     print(f"{name:62s}: {pw:6.0f} W  SM {clk['sm_mhz']:6.0f} MHz  {c / per:8.1f} cycles per {'MMA' if mode == 100 else 'tile-layer'}  {clk['reasons']}",
           flush=True)
