@@ -326,3 +326,38 @@ def test_fft_delayed_acceptance_on_a_long_trace_falls_back_to_the_cuda_core_coar
     assert res["flips"] == 0 and res["state_err"] == 0.0 and res["max_ll_err"] < 1e-3, res
     assert res["promoted"] > 0
     eng.close()
+
+
+# ----------------------------------------------------------------------------- K1 through the tensor-core pipeline
+@pytest.mark.parametrize("path", [0, 1, 2], ids=["fp32", "tc", "tc_coarse_on_cuda_cores"])
+def test_fft_surrogate_on_the_device_reproduces_the_tf_known_answer(path, monkeypatch):
+    """K1, directly on the device: the ten TensorFlow float32 predictions of `model_VoltageSignal_fft.keras` printed in
+    tests/Xaccelerometer_quality_factor/surrogate_fft.ipynb cell 11 are turned into coarse log-likelihoods with the reference's
+    reconstruction (cell 15) and compared with what the delayed-acceptance first stage computes for the same ten inputs.  On
+    the tensor-core path that stage IS the tcgen05 pipeline (three-way split layer-1 operand, five split hidden GEMMs with the
+    bias preloaded into the accumulator, the tanh / hi-lo epilogue, an N = 16 output GEMM): a direct TF pin of the hand-written
+    tensor-core arithmetic, not a transitive one."""
+    from mcmc_mems_b200 import engine as E
+    from oracle.coarse import features_to_trace
+    if path == 2:
+        monkeypatch.setenv("MEMS_COARSE_FP32", "1")
+        path = 1
+    pb = helpers.load_problem("qfactor")
+    cf = helpers.fft_coarse()
+    d = np.load(os.path.join(helpers.GOLDEN, "k1_fft.npz"))
+    X = d["X_test_scaled"].astype(np.float64) * cf["scaler_scale"] + cf["scaler_mean"]          # the ten inputs, unscaled
+    r = pb["y_obs"][None, :] - features_to_trace(d["tf_pred"], len(pb["y_obs"]))
+    want = -0.5 * np.sum(r * r, axis=1) / pb["sigma2"]                                            # from TF's own numbers
+    C = len(X)
+    x0 = np.tile(pb["x_opts"][0], (C, 1))
+    xi = (X - x0)[None, :, :]                                                                     # one update, scale 1
+    log_u = np.zeros((1, C, 2))
+    eng = helpers.engine(pb, C, path)
+    eng.set_coarse_fft(cf["layers"], cf["scaler_mean"], cf["scaler_scale"])
+    eng.set_sampler(E.SAMPLER_DA, da_stride=0)
+    eng.init_chains(x0, scale0=1.0)
+    _, llp, _ = eng.run_explicit(xi.transpose(0, 2, 1), log_u.transpose(0, 2, 1))
+    got = llp.cpu().numpy()[0, 0, :]
+    # TF printed ~7 significant digits of features of magnitude 1..1000: 1e-5 relative on the misfit they imply
+    assert np.allclose(got, want, rtol=3e-5, atol=0.05), (got, want)
+    eng.close()
