@@ -95,8 +95,8 @@ def ess(samples: torch.Tensor, max_lag: int = 0, group: Optional[dist.ProcessGro
     """Multi-chain effective sample size per parameter over every chain of every rank.
 
     The lag-autocovariance sums are computed on the device that holds the shard (``mems_chain_autocov``), one
-    all-reduce of ``P*(max_lag+2)+1`` doubles combines the ranks, Geyer's truncation runs on the host on a vector
-    of ``max_lag`` numbers.  Same estimator as arviz's ``ess`` without rank-normalisation (``diagnostics.ess_classic``).
+    all-reduce of ``P*(max_lag+2)+1`` doubles combines the ranks, Geyer's truncation runs on the device too
+    (``mems_ess_geyer``; host tensors -- the gloo tests -- take the numpy route).  Same estimator as arviz's ``ess`` without rank-normalisation (``diagnostics.ess_classic``).
     Returns ``(ess [P] numpy, truncated [P] bool)``."""
     import numpy as np
     from . import diagnostics
@@ -114,9 +114,18 @@ def ess(samples: torch.Tensor, max_lag: int = 0, group: Optional[dist.ProcessGro
     flat = torch.cat((sums.reshape(-1), torch.tensor([float(C_local)], dtype=torch.float64, device=sums.device)))
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat = flat.cpu().numpy()
-    Ct = int(round(flat[-1]))
-    tab = flat[:-1].reshape(P, L + 2)
+    Ct = int(round(float(flat[-1].item())))
+    if flat.is_cuda and L >= 2 and n >= 4:                           # Geyer's truncation where the sums live (mems_ess_geyer)
+        import ctypes as C
+        from . import _lib
+        tab = flat[:-1].reshape(P, L + 2).contiguous()
+        out = torch.empty(P, dtype=torch.float64, device=tab.device)
+        trunc = torch.empty(P, dtype=torch.int32, device=tab.device)
+        _lib.check(_lib.lib().mems_ess_geyer(tab.device.index or 0, C.c_void_p(tab.data_ptr()), P, L, n, Ct, C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(trunc.data_ptr()), C.c_void_p(torch.cuda.current_stream(tab.device).cuda_stream)),
+                   "mems_ess_geyer")
+        return out.cpu().numpy(), trunc.cpu().numpy().astype(bool)
+    tab = flat[:-1].cpu().numpy().reshape(P, L + 2)                  # host tensors: gloo tests of the reduction logic
     out, trunc = np.zeros(P), np.zeros(P, bool)
     for p in range(P):
         s1, s2 = tab[p, L], tab[p, L + 1]
